@@ -1,0 +1,302 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (via oracle/ref_shim.py).
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+Every fixture stores the seeded inputs (or the seed) and the reference's outputs; the tests compare the
+C / numpy oracle and -- on the GPU box -- the CUDA path against them.  Kept small (a few MB total).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from lvc_b200.config import DetectorConfig  # noqa: E402
+from lvc_b200.weights import synthetic_state_dict, synthetic_corrector_head  # noqa: E402
+from lvc_b200.testing import coco_like_boxes, distinct_scores  # noqa: E402
+
+
+def save(name, **arrs):
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **{k: (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
+def gold_batched_nms():
+    """detectron2.layers.batched_nms (nms.py:10-29) in all three regimes of the CPU reference run,
+    plus forced trick / vanilla torchvision branches (the CUDA reference run takes trick up to 25000 boxes)."""
+    from detectron2.layers import batched_nms, nms
+    from torchvision.ops import boxes as box_ops
+    rng = np.random.default_rng(11)
+    out = {}
+    for tag, n, ncls, thr in (("rpn900", 900, 5, 0.7), ("rpn4819", 4819, 5, 0.7), ("head3000", 3000, 80, 0.5),
+                              ("head900", 900, 80, 0.5), ("big41000", 41000, 80, 0.5)):
+        b = coco_like_boxes(rng, n)
+        s = distinct_scores(rng, n)
+        idx = rng.integers(0, ncls, n).astype(np.int64)
+        tb, ts, ti = torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(idx)
+        out[tag + "_boxes"], out[tag + "_scores"], out[tag + "_idxs"] = b, s, idx
+        out[tag + "_thr"] = np.float32(thr)
+        out[tag + "_keep_d2cpu"] = batched_nms(tb, ts, ti, thr)
+        if n < 40000:
+            out[tag + "_keep_trick"] = box_ops._batched_nms_coordinate_trick(tb, ts, ti, thr)
+            out[tag + "_keep_vanilla"] = box_ops._batched_nms_vanilla(tb, ts, ti, thr)
+        out[tag + "_keep_plain"] = nms(tb, ts, thr)
+    save("batched_nms", **out)
+
+
+def gold_roi_pooler():
+    """ROIPooler.forward (poolers.py:191-246) with the Base-RCNN-FPN settings (7x7, ratio 0, ROIAlignV2)."""
+    from detectron2.modeling.poolers import ROIPooler
+    from detectron2.structures import Boxes
+    rng = np.random.default_rng(12)
+    C, N = 8, 2
+    H, W = 96, 128  # image 96*4 x 128*4 = 384 x 512
+    feats = [torch.from_numpy(rng.standard_normal((N, C, H >> i, W >> i)).astype(np.float32)) for i in range(4)]
+    boxes = [coco_like_boxes(rng, 150, W=512, H=384), coco_like_boxes(rng, 90, W=512, H=384)]
+    # engineered edge cases on image 1: zero-size, inverted, fully outside, exact level boundaries
+    edge = np.array([[10, 10, 10, 10], [300, 300, 100, 100], [-50, -50, -20, -20], [0, 0, 112, 112], [0, 0, 224, 224],
+                     [0, 0, 448, 448], [0, 0, 111.99, 111.99], [5, 5, 511.9, 383.9], [500, 380, 700, 500]], np.float32)
+    boxes[1] = np.concatenate([boxes[1], edge], 0)
+    pooler = ROIPooler(output_size=7, scales=(1 / 4, 1 / 8, 1 / 16, 1 / 32), sampling_ratio=0, pooler_type="ROIAlignV2")
+    from detectron2.modeling.poolers import assign_boxes_to_levels
+    bl = [Boxes(torch.from_numpy(b)) for b in boxes]
+    out = pooler(feats, bl)
+    lv = assign_boxes_to_levels(bl, 2, 5, 224, 4)
+    save("roi_pooler", seed=12, C=C, N=N, H=H, W=W, boxes0=boxes[0], boxes1=boxes[1], levels=lv,
+         **{f"feat{i}": feats[i] for i in range(4)}, pooled=out)
+
+
+def gold_rpn_postproc():
+    """RPN decode + find_top_rpn_proposals (rpn.py:455-508; proposal_utils.py:13-118), CPU reference branch."""
+    from detectron2.modeling.anchor_generator import DefaultAnchorGenerator
+    from detectron2.modeling.box_regression import Box2BoxTransform
+    from detectron2.modeling.proposal_generator.proposal_utils import find_top_rpn_proposals
+    from detectron2.layers import ShapeSpec
+    rng = np.random.default_rng(13)
+    N = 2
+    image_sizes = [(320, 416), (300, 400)]
+    shapes = [(80, 104), (40, 52), (20, 26), (10, 13), (5, 7)]
+    ag = DefaultAnchorGenerator(sizes=[[32], [64], [128], [256], [512]], aspect_ratios=[[0.5, 1.0, 2.0]],
+                                strides=[4, 8, 16, 32, 64], offset=0.0)
+    feats = [torch.zeros(N, 1, h, w) for h, w in shapes]
+    anchors = ag(feats)
+    tr = Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0))
+    logits, deltas, props = [], [], []
+    total = sum(h * w * 3 for h, w in shapes) * N
+    allv = (rng.permutation(total).astype(np.float64) / total * 8 - 4).astype(np.float32)  # distinct across levels
+    assert len(np.unique(allv)) == total
+    cur = 0
+    for (h, w), a in zip(shapes, anchors):
+        n = h * w * 3
+        lg = allv[cur:cur + N * n].reshape(N, n)
+        cur += N * n
+        dl = (rng.standard_normal((N, n, 4)) * 0.5).astype(np.float32)
+        dl[0, :3] = np.array([[0, 0, 9, 9], [np.inf, 0, 0, 0], [0, 0, -30, -30]], np.float32)[: min(3, n)]
+        logits.append(torch.from_numpy(lg))
+        deltas.append(torch.from_numpy(dl))
+        at = a.tensor.unsqueeze(0).expand(N, -1, -1).reshape(-1, 4)
+        props.append(tr.apply_deltas(torch.from_numpy(dl).reshape(-1, 4), at).view(N, -1, 4))
+    res = find_top_rpn_proposals(props, logits, image_sizes, 0.7, 1000, 1000, 0.0, False)
+    out = dict(image_sizes=np.array(image_sizes), shapes=np.array(shapes))
+    for i in range(5):
+        out[f"logits{i}"], out[f"deltas{i}"] = logits[i], deltas[i]
+        out[f"anchors{i}"] = anchors[i].tensor
+    for n in range(N):
+        out[f"prop_boxes{n}"] = res[n].proposal_boxes.tensor
+        out[f"prop_logits{n}"] = res[n].objectness_logits
+    save("rpn_postproc", **out)
+
+
+def gold_fast_rcnn_inference():
+    """FastRCNNOutputs.predict_boxes/predict_probs + fast_rcnn_inference (fast_rcnn.py:51-137,440-493)."""
+    from lvc.modeling.roi_heads.fast_rcnn import fast_rcnn_inference
+    from detectron2.modeling.box_regression import Box2BoxTransform
+    import torch.nn.functional as F
+    rng = np.random.default_rng(14)
+    R, K = 300, 80
+    image_shape = (800, 1333)
+    props = coco_like_boxes(rng, R)
+    logits = (rng.standard_normal((R, K + 1)) * 2.0).astype(np.float32)
+    deltas = (rng.standard_normal((R, K * 4)) * 0.7).astype(np.float32)
+    tr = Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0))
+    boxes = tr.apply_deltas(torch.from_numpy(deltas).view(R * K, 4),
+                            torch.from_numpy(props).unsqueeze(1).expand(R, K, 4).reshape(-1, 4)).view(R, K * 4)
+    probs = F.softmax(torch.from_numpy(logits), dim=-1)
+    out = dict(props=props, logits=logits, deltas=deltas, boxes=boxes.clone(), probs=probs.clone(), image_shape=np.array(image_shape))
+    for tag, thr in (("t05", 0.05), ("t00", 0.0)):
+        inst, kept = fast_rcnn_inference([boxes.clone()], [probs.clone()], [image_shape], thr, 0.5, 100)  # Boxes.clip mutates its input
+        out[tag + "_boxes"] = inst[0].pred_boxes.tensor
+        out[tag + "_scores"] = inst[0].scores
+        out[tag + "_classes"] = inst[0].pred_classes
+        out[tag + "_rows"] = kept[0]
+    save("fast_rcnn_inference", **out)
+
+
+def gold_knn():
+    """run_nearest_neighbours + get_nn_class_confirmatory (tools/run_nearest_neighbours.py:142-162,214-227)."""
+    import importlib
+    tool = importlib.import_module("tools.run_nearest_neighbours")
+    from detectron2.structures import Instances
+    rng = np.random.default_rng(15)
+    S, D, ncls = 120, 256, 20
+    cls = np.repeat(np.arange(ncls), S // ncls).astype(np.int64)
+    means = (rng.standard_normal((ncls, D)) * 0.25).astype(np.float32)
+    bank = (rng.standard_normal((S, D)).astype(np.float32) + means[cls])
+    qf = []
+    qcls_all, feats_all = [], []
+    for i in range(40):
+        q = int(rng.integers(1, 8))
+        qc = rng.integers(0, ncls, q).astype(np.int64)
+        f = rng.standard_normal((q, D)).astype(np.float32) + means[(qc + (rng.random(q) < 0.3)) % ncls]
+        inst = Instances((10, 10))
+        inst.set("crop_feats", torch.from_numpy(f))
+        inst.set("gt_classes", torch.from_numpy(qc))
+        qf.append({"instances": inst})
+        qcls_all.append(qc)
+        feats_all.append(f)
+    # engineered: a zero query and a query equal to the bank mean (cosine -> 0 everywhere)
+    tool.tqdm = lambda x, **k: x
+    res = tool.run_nearest_neighbours(torch.from_numpy(cls), torch.from_numpy(bank), qf, cosine=True)
+    out = dict(bank=bank, bank_cls=cls, queries=np.concatenate(feats_all), query_cls=np.concatenate(qcls_all),
+               counts=np.array([len(x) for x in qcls_all]))
+    out["votes"] = torch.cat([d["instances"].top10_shots for d in res])
+    for k in (10, 5, 1):
+        tool.get_nn_class_confirmatory(res, k)
+        out[f"keep_k{k}"] = torch.cat([d["instances"].keep for d in res])
+    save("knn", **out)
+
+
+def _images(seed, sizes):
+    ims = []
+    for i, (h, w) in enumerate(sizes):
+        g = torch.Generator().manual_seed(seed + i)
+        ims.append(torch.rand(3, h, w, generator=g) * 255)
+    return ims
+
+
+def gold_e2e(tag, config_rel, depth, sizes, out_sizes, opts=()):
+    """GeneralizedRCNN.inference (rcnn.py:177-322) end to end with lvc_b200.weights synthetic weights loaded
+    strict=True into the reference model."""
+    cfg, model = ref_shim.build_reference_model(config_rel, ["MODEL.RESNETS.DEPTH", depth] + list(opts), calibrate=False)
+    dcfg = DetectorConfig.from_reference_cfg(cfg)
+    sd = synthetic_state_dict(dcfg, seed=0)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys, missing.unexpected_keys
+    assert all("cell_anchors" in k for k in missing.missing_keys), missing.missing_keys
+    ims = _images(100, sizes)
+    inputs = [{"image": im, "height": oh, "width": ow} for im, (oh, ow) in zip(ims, out_sizes)]
+    cap = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            cap[name] = out
+        return f
+    model.backbone.register_forward_hook(hook("features"))
+    model.proposal_generator.register_forward_hook(hook("proposals"))
+    model.roi_heads.box_pooler.register_forward_hook(hook("pooled"))
+    model.roi_heads.box_head.register_forward_hook(hook("head"))
+    model.roi_heads.box_predictor.register_forward_hook(hook("pred"))
+    with torch.no_grad():
+        res = model(inputs)
+    out = dict(sizes=np.array(sizes), out_sizes=np.array(out_sizes), seed=100, depth=depth,
+               output_layer=dcfg.output_layer, score_thresh=dcfg.score_thresh_test)
+    rng = np.random.default_rng(5)
+    for k, v in cap["features"].items():
+        flat = v.flatten()
+        idx = rng.integers(0, flat.numel(), 2048)
+        out[f"feat_{k}_idx"], out[f"feat_{k}_val"] = idx, flat[idx]
+        out[f"feat_{k}_absmean"] = v.abs().mean()
+    props = cap["proposals"][0]
+    for n, p in enumerate(props):
+        out[f"prop_boxes{n}"] = p.proposal_boxes.tensor
+        out[f"prop_logits{n}"] = p.objectness_logits
+    pooled = cap["pooled"]
+    idx = rng.integers(0, pooled.numel(), 4096)
+    out["pooled_idx"], out["pooled_val"], out["pooled_shape"] = idx, pooled.flatten()[idx], np.array(pooled.shape)
+    out["head_sample"] = cap["head"][:64, :64]
+    out["cls_logits_sample"] = cap["pred"][0][:128]
+    out["box_deltas_sample"] = cap["pred"][1][:128, :16]
+    for n, r in enumerate(res):
+        inst = r["instances"]
+        out[f"det_boxes{n}"] = inst.pred_boxes.tensor
+        out[f"det_scores{n}"] = inst.scores
+        out[f"det_classes{n}"] = inst.pred_classes
+    print(tag, "detections", [len(r["instances"]) for r in res], "proposals", [len(p) for p in props])
+    save("e2e_" + tag, **out)
+
+
+def gold_corrector():
+    """Box corrector: GeneralizedRCNN + CascadeROIHeads/BoxOnlyLayersCascade (cascade_rcnn.py:167-203) driven
+    through CascadeROIHeads._forward_box_qe on fixed FPN features."""
+    from detectron2.structures import Boxes, Instances, ImageList
+    cfg, model = ref_shim.build_reference_model(
+        "COCO-detection/cascade_ubbr_R_50_FPN_ft_all_30shot_aug_ftmore.yaml",
+        ["QUERY_EXPAND.ENABLED", True], calibrate=False)
+    dcfg = DetectorConfig(depth=50, num_fc=3)
+    sd = synthetic_corrector_head(dcfg, seed=3)
+    # give bbox_pred a larger scale so that corrections are visible
+    for k in list(sd):
+        if "bbox_pred.weight" in k:
+            sd[k] = sd[k] * 30
+    miss = model.roi_heads.load_state_dict({k[len("roi_heads."):]: v for k, v in sd.items()}, strict=True)
+    rng = np.random.default_rng(16)
+    N, C = 1, 256
+    H, W = 24, 32
+    image_sizes = [(96, 128)]
+    # features rounded to fp16 so the fixture stores them exactly in half the bytes
+    feats = {f"p{l}": torch.from_numpy((rng.standard_normal((N, C, H >> i, W >> i)) * 0.5).astype(np.float16).astype(np.float32))
+             for i, l in enumerate((2, 3, 4, 5))}
+    boxes = [coco_like_boxes(rng, 48, W=128, H=96, min_side=4, max_side=120)]
+    classes = [rng.integers(0, 80, len(b)).astype(np.int64) for b in boxes]
+    targets = []
+    for b, c, s in zip(boxes, classes, image_sizes):
+        inst = Instances(s)
+        inst.gt_boxes = Boxes(torch.from_numpy(b))
+        inst.gt_classes = torch.from_numpy(c)
+        targets.append(inst)
+    with torch.no_grad():
+        res, _ = model.roi_heads._forward_box_qe(feats, None, targets)
+    out = dict(image_sizes=np.array(image_sizes), seed_head=3, scale=30)
+    for k, v in feats.items():
+        out["feat_" + k] = v.numpy().astype(np.float16)
+    for n in range(N):
+        out[f"boxes{n}"], out[f"classes{n}"] = boxes[n], classes[n]
+        out[f"out_boxes{n}"] = res[n].pred_boxes.tensor
+        out[f"out_classes{n}"] = res[n].pred_classes
+    save("box_corrector", **out)
+
+
+def main():
+    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector"]
+    if "nms" in which:
+        gold_batched_nms()
+    if "pooler" in which:
+        gold_roi_pooler()
+    if "rpn" in which:
+        gold_rpn_postproc()
+    if "frcnn" in which:
+        gold_fast_rcnn_inference()
+    if "knn" in which:
+        gold_knn()
+    if "corrector" in which:
+        gold_corrector()
+    if "e2e" in which:
+        # config #1 family: Base-RCNN-FPN R50 (FastRCNNOutputLayers), two ragged images
+        gold_e2e("r50_base", "Base-RCNN-FPN.yaml", 50, [(320, 416), (300, 400)], [(480, 624), (300, 400)])
+        # candidate-sourcing config (CosineSimOutputLayers), R101, one image
+        gold_e2e("r101_cosine", "COCO-detection/faster_rcnn_R_50_FPN_ft_all_30shot_aug_ftmore_dropout.yaml", 101,
+                 [(256, 320)], [(256, 320)])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,321 @@
+"""CPU oracle for the LVC pseudo-label mining hot path (python side).
+
+TEST INFRASTRUCTURE ONLY -- the checker for lvc_b200's CUDA path.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / ``--impl reference`` legs may import this module.
+
+Integer / index / byte decisions (NMS, level assignment, top-k, vote) are computed by the scalar C
+restatement in ``lvc_oracle.c`` (loaded through ctypes); this file holds the glue that strings those
+pieces together exactly the way the reference's Python does, plus a dense fp32 restatement of the
+detector (conv / linear through torch's CPU kernels, which is the very library layer the reference
+itself calls: detectron2/layers/wrappers.py:94-98 -> F.conv2d).
+
+Parity pinning: see the header of lvc_oracle.c and tests/test_oracle_golden.py.
+Reference citations are relative to /root/reference (prannaykaul/lvc @ 3b5e5fa).
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblvc_oracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force=False):
+    """gcc-compile lvc_oracle.c -> liblvc_oracle.so (in oracle/, git-ignored)."""
+    src = os.path.join(_HERE, "lvc_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(
+            ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden",
+             "-o", _SO, src, "-lm"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.orc_nms.restype = ctypes.c_int64
+        _lib.orc_batched_nms.restype = ctypes.c_int64
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+# ------------------------------------------------------------------------------------ RoIAlign
+def roi_align(inp, rois, output_size, spatial_scale, sampling_ratio, aligned):
+    """detectron2/layers/roi_align.py:63-108 -> torchvision.ops.roi_align; NCHW fp32."""
+    inp = _f32(inp)
+    rois = _f32(rois).reshape(-1, 5)
+    N, C, H, W = inp.shape
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    out = np.zeros((rois.shape[0], C, ph, pw), np.float32)
+    if rois.shape[0]:
+        lib().orc_roi_align_forward(_p(inp, _f32p), N, C, H, W, _p(rois, _f32p), rois.shape[0], ph, pw,
+                                    ctypes.c_float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                                    _p(out, _f32p))
+    return out
+
+
+def assign_boxes_to_levels(boxes, min_level=2, max_level=5, canonical_box_size=224, canonical_level=4):
+    """detectron2/modeling/poolers.py:23-59."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    out = np.zeros(boxes.shape[0], np.int64)
+    lib().orc_assign_boxes_to_levels(_p(boxes, _f32p), boxes.shape[0], min_level, max_level,
+                                     canonical_box_size, canonical_level, _p(out, _i64p))
+    return out
+
+
+def roi_pooler(features, box_lists, output_size=7, scales=(0.25, 0.125, 0.0625, 0.03125),
+               sampling_ratio=0, canonical_box_size=224, canonical_level=4):
+    """ROIPooler.forward, detectron2/modeling/poolers.py:191-246 (pooler type ROIAlignV2: aligned=True).
+
+    features: list of NCHW arrays; box_lists: list (per image) of [Ri,4] arrays.
+    Returns (pooled [M,C,s,s], level_assignments [M]).
+    """
+    min_level = int(-math.log2(scales[0]))
+    max_level = int(-math.log2(scales[-1]))
+    fmt = np.concatenate(
+        [np.concatenate([np.full((len(b), 1), i, np.float32), _f32(b).reshape(-1, 4)], 1)
+         for i, b in enumerate(box_lists)], 0)
+    allb = np.concatenate([_f32(b).reshape(-1, 4) for b in box_lists], 0)
+    if len(scales) == 1:
+        return roi_align(features[0], fmt, output_size, scales[0], sampling_ratio, True), np.zeros(len(fmt), np.int64)
+    lvls = assign_boxes_to_levels(allb, min_level, max_level, canonical_box_size, canonical_level)
+    C = features[0].shape[1]
+    out = np.zeros((len(fmt), C, output_size, output_size), np.float32)
+    for level, scale in enumerate(scales):
+        inds = np.nonzero(lvls == level)[0]
+        out[inds] = roi_align(features[level], fmt[inds], output_size, scale, sampling_ratio, True)
+    return out, lvls
+
+
+# ------------------------------------------------------------------------------------ NMS
+def nms(boxes, scores, thr):
+    """torchvision.ops.nms as reached from detectron2/layers/nms.py:7,25."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores)
+    keep = np.zeros(len(scores), np.int64)
+    n = lib().orc_nms(_p(boxes, _f32p), _p(scores, _f32p), ctypes.c_int64(len(scores)), ctypes.c_float(thr),
+                      _p(keep, _i64p))
+    return keep[:n].copy()
+
+
+TRICK, VANILLA = 0, 1
+
+
+def nms_mode_for(n_boxes, device="cuda"):
+    """Which branch the reference takes for ``n_boxes`` (detectron2/layers/nms.py:19-29 on top of
+    torchvision.ops.boxes.batched_nms of torchvision 0.26: trick iff numel <= 4000 (cpu) / 100000 (cuda))."""
+    if n_boxes >= 40000:
+        return VANILLA
+    limit = 4000 if device == "cpu" else 100_000
+    return VANILLA if n_boxes * 4 > limit else TRICK
+
+
+def batched_nms(boxes, scores, idxs, thr, mode=None, device="cuda"):
+    """detectron2/layers/nms.py:10-29.  mode None = the branch the reference would take on ``device``."""
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores)
+    idxs = _i64(idxs)
+    if mode is None:
+        mode = nms_mode_for(len(scores), device)
+    keep = np.zeros(len(scores), np.int64)
+    n = lib().orc_batched_nms(_p(boxes, _f32p), _p(scores, _f32p), _p(idxs, _i64p), ctypes.c_int64(len(scores)),
+                              ctypes.c_float(thr), int(mode), _p(keep, _i64p))
+    return keep[:n].copy()
+
+
+# ------------------------------------------------------------------------------------ boxes / anchors
+SCALE_CLAMP = math.log(1000.0 / 16)  # detectron2/modeling/box_regression.py:14
+
+
+def apply_deltas(deltas, boxes, weights):
+    """Box2BoxTransform.apply_deltas, detectron2/modeling/box_regression.py:73-110."""
+    deltas = _f32(deltas)
+    boxes = _f32(boxes).reshape(-1, 4)
+    R = boxes.shape[0]
+    deltas = deltas.reshape(R, -1)
+    K = deltas.shape[1] // 4
+    out = np.zeros_like(deltas)
+    if R:
+        lib().orc_apply_deltas(_p(deltas, _f32p), _p(boxes, _f32p), R, K, *[ctypes.c_float(w) for w in weights],
+                               ctypes.c_float(SCALE_CLAMP), _p(out, _f32p))
+    return out
+
+
+def clip_boxes(boxes, image_size):
+    """Boxes.clip, detectron2/structures/boxes.py:183-196.  image_size = (h, w)."""
+    b = _f32(boxes).reshape(-1, 4).copy()
+    lib().orc_clip_boxes(_p(b, _f32p), ctypes.c_int64(len(b)), int(image_size[0]), int(image_size[1]))
+    return b
+
+
+def nonempty(boxes, threshold=0.0):
+    """Boxes.nonempty, detectron2/structures/boxes.py:198-212."""
+    b = _f32(boxes).reshape(-1, 4)
+    return ((b[:, 2] - b[:, 0]) > threshold) & ((b[:, 3] - b[:, 1]) > threshold)
+
+
+def cell_anchors(sizes, ratios):
+    """generate_cell_anchors, detectron2/modeling/anchor_generator.py:173-208."""
+    s = np.ascontiguousarray(sizes, np.float64)
+    r = np.ascontiguousarray(ratios, np.float64)
+    out = np.zeros((len(s) * len(r), 4), np.float32)
+    lib().orc_cell_anchors(_p(s, _f64p), len(s), _p(r, _f64p), len(r), _p(out, _f32p))
+    return out
+
+
+def grid_anchors(cell, H, W, stride):
+    """_grid_anchors, detectron2/modeling/anchor_generator.py:157-171 (offset 0)."""
+    cell = _f32(cell)
+    out = np.zeros((H * W * len(cell), 4), np.float32)
+    lib().orc_grid_anchors(_p(cell, _f32p), len(cell), H, W, stride, _p(out, _f32p))
+    return out
+
+
+# ------------------------------------------------------------------------------------ RPN post-processing
+def find_top_rpn_proposals(proposals, logits, image_sizes, nms_thresh=0.7, pre_nms_topk=1000,
+                           post_nms_topk=1000, min_box_size=0.0, nms_mode=None, device="cuda"):
+    """detectron2/modeling/proposal_generator/proposal_utils.py:13-118 (inference branch).
+
+    proposals: list over levels of [N, HWA, 4]; logits: list of [N, HWA].
+    Returns per image (boxes [K,4], logits [K]).  Sort ties: lower index first (stable).
+    """
+    N = len(image_sizes)
+    tk_scores, tk_props, lvl_ids = [], [], []
+    for level_id, (p, l) in enumerate(zip(proposals, logits)):
+        k = min(pre_nms_topk, l.shape[1])
+        idx = np.argsort(-_f32(l), axis=1, kind="stable")[:, :k]
+        tk_scores.append(np.take_along_axis(_f32(l), idx, 1))
+        tk_props.append(np.take_along_axis(_f32(p), idx[:, :, None], 1))
+        lvl_ids.append(np.full(k, level_id, np.int64))
+    tk_scores = np.concatenate(tk_scores, 1)
+    tk_props = np.concatenate(tk_props, 1)
+    lvl_ids = np.concatenate(lvl_ids)
+    res = []
+    for n in range(N):
+        boxes, sc, lvl = tk_props[n], tk_scores[n], lvl_ids
+        valid = np.isfinite(boxes).all(1) & np.isfinite(sc)
+        boxes, sc, lvl = boxes[valid], sc[valid], lvl[valid]
+        boxes = clip_boxes(boxes, image_sizes[n])
+        keep = nonempty(boxes, min_box_size)
+        boxes, sc, lvl = boxes[keep], sc[keep], lvl[keep]
+        k = batched_nms(boxes, sc, lvl, nms_thresh, mode=nms_mode, device=device)[:post_nms_topk]
+        res.append((boxes[k], sc[k]))
+    return res
+
+
+# ------------------------------------------------------------------------------------ box-head post-processing
+def softmax_rows(x):
+    x = _f32(x)
+    out = np.zeros_like(x)
+    lib().orc_softmax_rows(_p(x, _f32p), ctypes.c_int64(x.shape[0]), x.shape[1], _p(out, _f32p))
+    return out
+
+
+def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image,
+                                     nms_mode=None, device="cuda"):
+    """lvc/modeling/roi_heads/fast_rcnn.py:95-137.  boxes [R, K*4] (or [R,4]), scores [R, K+1].
+
+    Returns (pred_boxes [n,4], scores [n], pred_classes [n], kept_row_idx [n]).
+    """
+    scores = _f32(scores)[:, :-1]
+    nreg = boxes.shape[1] // 4
+    b = clip_boxes(_f32(boxes).reshape(-1, 4), image_shape).reshape(-1, nreg, 4)
+    mask = scores > np.float32(score_thresh)
+    r_idx, c_idx = np.nonzero(mask)
+    bsel = b[r_idx, 0] if nreg == 1 else b[mask]
+    ssel = scores[mask]
+    keep = batched_nms(bsel, ssel, c_idx, nms_thresh, mode=nms_mode, device=device)
+    if topk_per_image >= 0:
+        keep = keep[:topk_per_image]
+    return bsel[keep], ssel[keep], c_idx[keep].astype(np.int64), r_idx[keep].astype(np.int64)
+
+
+def detector_postprocess(boxes, image_size, out_h, out_w):
+    """detectron2/modeling/postprocessing.py:10-79 (boxes only).  Returns (scaled+clipped boxes, keep mask)."""
+    sx, sy = out_w / image_size[1], out_h / image_size[0]
+    b = _f32(boxes).reshape(-1, 4).copy()
+    b[:, 0::2] *= np.float32(sx)
+    b[:, 1::2] *= np.float32(sy)
+    b = clip_boxes(b, (out_h, out_w))
+    return b, nonempty(b)
+
+
+# ------------------------------------------------------------------------------------ kNN label verification
+def knn_verify(bank, bank_cls, queries, query_cls, topk=10, knn=10):
+    """tools/run_nearest_neighbours.py:142-162 + :214-227.
+
+    Returns dict(top_idx [Q,topk], top_sim, votes, nn_class [Q], keep [Q] uint8)."""
+    bank = _f32(bank)
+    queries = _f32(queries)
+    bank_cls = _i64(bank_cls)
+    query_cls = _i64(query_cls)
+    Q, D = queries.shape
+    S = bank.shape[0]
+    top_idx = np.full((Q, topk), -1, np.int64)
+    top_sim = np.zeros((Q, topk), np.float32)
+    votes = np.zeros((Q, topk), np.int64)
+    nn_class = np.zeros(Q, np.int64)
+    keep = np.zeros(Q, np.uint8)
+    lib().orc_knn_verify(_p(bank, _f32p), _p(bank_cls, _i64p), S, D, _p(queries, _f32p), _p(query_cls, _i64p),
+                         ctypes.c_int64(Q), topk, knn, _p(top_idx, _i64p), _p(top_sim, _f32p), _p(votes, _i64p),
+                         _p(nn_class, _i64p), _p(keep, _u8p))
+    return dict(top_idx=top_idx, top_sim=top_sim, votes=votes, nn_class=nn_class, keep=keep)
+
+
+def knn_verify_batched_torch(bank, bank_cls, queries, query_cls, topk=10, knn=10, chunk=8192):
+    """Same result through torch CPU matmul (multi-threaded) -- used as the *fast* CPU baseline form
+    (BASELINE.md section 2 'batched-GEMM form'); the scalar C version above is the checker."""
+    import torch
+    bank = torch.as_tensor(bank, dtype=torch.float32)
+    q = torch.as_tensor(queries, dtype=torch.float32)
+    mu = bank.mean(0, keepdim=True)
+    bn = torch.nn.functional.normalize(bank - mu, dim=1, eps=1e-8)
+    bcls = torch.as_tensor(bank_cls)
+    outs = []
+    for s in range(0, q.shape[0], chunk):
+        qn = torch.nn.functional.normalize(q[s:s + chunk] - mu, dim=1, eps=1e-8)
+        outs.append((qn @ bn.t()).topk(topk, dim=1)[1])
+    idx = torch.cat(outs)
+    votes = bcls[idx]
+    nn_class = torch.mode(votes[:, :knn], dim=1)[0]
+    keep = (nn_class == torch.as_tensor(query_cls)).to(torch.uint8)
+    return dict(top_idx=idx.numpy(), votes=votes.numpy(), nn_class=nn_class.numpy(), keep=keep.numpy())
+
+
+def knn_reference_form_torch(bank, bank_cls, queries, per_call=5, topk=10):
+    """The reference's literal per-image broadcast form (run_nearest_neighbours.py:146-161), Q=per_call
+    queries per call -- the honest 'reference CPU path' for timing."""
+    import torch
+    import torch.nn.functional as F
+    bank = torch.as_tensor(bank, dtype=torch.float32)
+    q = torch.as_tensor(queries, dtype=torch.float32)
+    bcls = torch.as_tensor(bank_cls)
+    crop_mean = bank.mean(dim=0, keepdim=True)
+    out = []
+    for s in range(0, q.shape[0], per_call):
+        qf = q[s:s + per_call]
+        sim = F.cosine_similarity(bank.sub(crop_mean).unsqueeze(0).float(), qf.sub(crop_mean).unsqueeze(1).float(), dim=-1)
+        out.append(bcls[sim.topk(topk, dim=-1)[1]])
+    return torch.cat(out).numpy()
