@@ -1,0 +1,220 @@
+/*
+ * lvcb200.h -- C ABI of liblvcb200.so, the B200 (sm_100a) implementation of the LVC pseudo-label
+ * mining hot path (prannaykaul/lvc @ 3b5e5fa).
+ *
+ * The reference has no C ABI on this path: it is a Python import surface (detectron2.layers /
+ * lvc.modeling) over torch / torchvision ops.  Each entry point below therefore cites
+ * the reference *Python* interface it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds
+ * on the reference side.  Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless it says "host";
+ *   - never allocates, never synchronises the device (except where stated); work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - returns 0 on success, a cudaError_t (>0) on a CUDA failure, or a negative LVCB200_E* code;
+ *     lvcb200_last_error() returns a thread-local message;
+ *   - inputs are never modified; outputs are fully written;
+ *   - empty inputs (0 boxes / 0 rois / 0 queries) are valid and return 0 (roi_align.py / nms.py behaviour).
+ */
+#ifndef LVCB200_H_
+#define LVCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define LVCB200_ABI_VERSION 1
+#define LVCB200_EINVAL (-1)      /* bad argument (shape, alignment, NULL) */
+#define LVCB200_EWORKSPACE (-2)  /* workspace too small */
+#define LVCB200_EUNSUPPORTED (-3)
+
+int lvcb200_abi_version(void);
+const char* lvcb200_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench: gpu_launches) */
+int64_t lvcb200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * RoIAlign, reference layout.  Replaces detectron2.layers.roi_align / ROIAlign.forward
+ * (detectron2/layers/roi_align.py:14-15,63-108 -> torchvision.ops.roi_align; arithmetic spec
+ * detectron2/layers/csrc/ROIAlign/ROIAlign_cuda.cu:12-139).
+ * input [N,C,H,W] fp32 contiguous; rois [R,5] = (batch_idx, x1, y1, x2, y2) fp32; output [R,C,ph,pw] fp32.
+ * ------------------------------------------------------------------------------------------------- */
+int lvcb200_roi_align_nchw_f32(const float* input, int N, int C, int H, int W, const float* rois, int R,
+                               int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
+                               float* output, void* stream);
+
+/* FPN level assignment.  Replaces assign_boxes_to_levels (detectron2/modeling/poolers.py:23-59).
+ * boxes [R,4] fp32 -> levels [R] int64 (level - min_level). */
+int lvcb200_assign_boxes_to_levels(const float* boxes, int64_t R, int min_level, int max_level,
+                                   int canonical_box_size, int canonical_level, int64_t* levels, void* stream);
+
+/* One feature-map level in channels-last storage: element (n, y, x, c) lives at
+ * base[((n * img_stride) + y * row_stride + x) * C_stride + c]   (strides in pixels / elements),
+ * which covers both dense NHWC and the zero-bordered planes the conv engine writes. */
+typedef struct {
+  const void* base;     /* bf16 or fp32, see `dtype` of the call */
+  int H, W;             /* valid extent */
+  int64_t img_stride;   /* pixels between images */
+  int64_t row_stride;   /* pixels between rows */
+  int64_t c_stride;     /* elements per pixel (>= C) */
+  float spatial_scale;  /* 1/stride of this level */
+} lvcb200_fmap;
+
+#define LVCB200_F32 0
+#define LVCB200_BF16 1
+#define LVCB200_OUT_NCHW 0 /* [R, C, ph, pw]  (reference order; fc1 weight index c*49+h*7+w) */
+#define LVCB200_OUT_NHWC 1 /* [R, ph, pw, C]  (engine order; fc1 weight permuted at load time) */
+
+/* Fused multi-level pooler.  Replaces ROIPooler.forward (detectron2/modeling/poolers.py:191-246):
+ * convert_boxes_to_pooler_format + assign_boxes_to_levels + per-level ROIAlign(aligned=True) + scatter,
+ * in ONE launch, no host sync.  rois [R,5]; levels_out (optional, may be NULL) [R] int64.
+ * out: [R, C*ph*pw] elements of out_dtype in out_layout, row pitch out_pitch elements. */
+int lvcb200_roi_pool_fpn(const lvcb200_fmap* levels /*host*/, int n_levels, int in_dtype, int C, const float* rois,
+                         int64_t R, int pooled, int sampling_ratio, int canonical_box_size, int canonical_level,
+                         int min_level, void* out, int out_dtype, int out_layout, int64_t out_pitch,
+                         int64_t* levels_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * NMS.  Replaces detectron2.layers.nms / batched_nms (detectron2/layers/nms.py:7,10-29 ->
+ * torchvision.ops.nms / batched_nms).  boxes [n,4] fp32, scores [n] fp32, idxs [n] int64 or NULL (plain nms).
+ * mode: 0 = coordinate trick (boxes + idx*(max+1) in fp32, the branch the reference takes on CUDA for
+ *           n <= 25000), 1 = vanilla per-class (n > 25000, and nms.py:22-29 for n >= 40000),
+ *       -1 = pick like the reference would on a CUDA device.
+ * keep [n] int64: kept original indices in descending score order (ties: lower index first);
+ * num_keep: device int64 scalar.  workspace: device scratch of >= lvcb200_batched_nms_workspace(n) bytes.
+ * ------------------------------------------------------------------------------------------------- */
+size_t lvcb200_batched_nms_workspace(int64_t n);
+int lvcb200_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_threshold,
+                        int mode, int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * RPN post-processing.  Replaces RPN.predict_proposals (detectron2/modeling/proposal_generator/rpn.py:455-508)
+ * = DefaultAnchorGenerator (anchor_generator.py:157-208) + Box2BoxTransform.apply_deltas
+ * (box_regression.py:73-110) + find_top_rpn_proposals (proposal_utils.py:13-118), inference branch.
+ * Per level l: logits element (n,y,x,a) at logits[n*img_stride + (y*W + x)*pix_stride + a] when
+ * row_stride == 0, else at logits[n*img_stride + y*row_stride + x*pix_stride + a]; deltas likewise with
+ * (a*4 + coord).  Only the selected top-k anchors are decoded.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* logits;
+  const float* deltas;
+  int H, W, A;
+  int stride;                 /* anchor stride in pixels (4,8,16,32,64) */
+  int64_t img_stride_l, row_stride_l, pix_stride_l; /* logits strides (elements) */
+  int64_t img_stride_d, row_stride_d, pix_stride_d; /* deltas strides (elements) */
+  float cell_anchors[3 * 4];  /* A x (x1,y1,x2,y2), generate_cell_anchors values (A <= 3) */
+} lvcb200_rpn_level;
+
+typedef struct {
+  int n_images, n_levels;
+  int pre_nms_topk, post_nms_topk;
+  float nms_thresh, min_box_size;
+  float weights[4];           /* Box2BoxTransform weights */
+  int nms_mode;               /* as lvcb200_batched_nms */
+} lvcb200_rpn_params;
+
+size_t lvcb200_rpn_proposals_workspace(const lvcb200_rpn_params* p /*host*/);
+/* image_sizes [n_images,2] int32 (h, w) device.  Outputs: proposals [n_images, post_nms_topk, 4] fp32,
+ * prop_logits [n_images, post_nms_topk] fp32, counts [n_images] int32 (rows beyond count are zero). */
+int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels /*host*/, const lvcb200_rpn_params* p /*host*/,
+                          const int32_t* image_sizes, float* proposals, float* prop_logits, int32_t* counts,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Box-head post-processing.  Replaces FastRCNNOutputs.predict_boxes / predict_probs / inference
+ * (lvc/modeling/roi_heads/fast_rcnn.py:440-493), fast_rcnn_inference_single_image (:95-137) and
+ * detector_postprocess (detectron2/modeling/postprocessing.py:10-79).
+ * cls_logits [R, K+1] (row pitch logit_pitch), box_deltas [R, 4K] (pitch delta_pitch) or [R,4]
+ * (class_agnostic), proposals [R,4], roi_image [R] int32 image index of each row (rows grouped by image,
+ * at most max_rois_per_image per image).  row_scale (optional) multiplies the logits of row r (cosine head).
+ * image_sizes [n_images,2] int32 (h,w) network input size; out_sizes [n_images,2] int32 requested output size.
+ * Outputs per image, padded to topk: det_boxes [n_images, topk, 4], det_scores, det_classes (int64),
+ * det_rows (int64, row index within the image), det_counts [n_images] int32.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n_images, num_classes, max_rois_per_image, class_agnostic;
+  float weights[4];
+  float score_thresh, nms_thresh;
+  int topk_per_image;
+  int nms_mode;
+} lvcb200_det_params;
+
+size_t lvcb200_detections_workspace(const lvcb200_det_params* p /*host*/);
+int lvcb200_detections(const float* cls_logits, int64_t logit_pitch, const float* row_scale, const float* box_deltas,
+                       int64_t delta_pitch, const float* proposals, const int32_t* roi_image, int64_t R,
+                       const lvcb200_det_params* p /*host*/, const int32_t* image_sizes, const int32_t* out_sizes,
+                       float* det_boxes, float* det_scores, int64_t* det_classes, int64_t* det_rows, int32_t* det_counts,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * kNN label verification.  Replaces run_nearest_neighbours + get_nn_class_confirmatory
+ * (tools/run_nearest_neighbours.py:142-162, 214-227): centred cosine similarity against the support bank,
+ * top-`topk` neighbours, class votes, mode over the first `knn` votes (smallest class on ties),
+ * keep = (mode == detector class).
+ * bank [S,D] fp32, bank_cls [S] int64, queries [Q,D] fp32, query_cls [Q] int64.
+ * Outputs: top_idx [Q,topk] int64 (bank rows, best first), votes [Q,topk] int64, keep [Q] uint8;
+ * top_sim [Q,topk] fp32 optional (NULL to skip).  S <= 4096, topk <= 16, D % 4 == 0.
+ * lvcb200_knn_prepare centres/normalises the bank once (after the all-gather); bank_prepared holds
+ * lvcb200_knn_prepared_bytes(S,D) bytes.
+ * ------------------------------------------------------------------------------------------------- */
+size_t lvcb200_knn_prepared_bytes(int S, int D);
+int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_prepared, void* stream);
+int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
+                       const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
+                       int64_t* votes, uint8_t* keep, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense layers: tcgen05 / TMEM / TMA GEMM with row-shifted A operands ("shift-GEMM"), which is how the
+ * engine runs every conv of the ResNet-FPN stack (detectron2/layers/wrappers.py:94-98 Conv2d.forward +
+ * FrozenBatchNorm2d.forward batch_norm.py:45-65 + relu, resnet.py:195-211), the RPN head (rpn.py:120-139),
+ * the box head FCs (lvc/modeling/roi_heads/box_head.py:82-91) and the predictors (fast_rcnn.py:583-598).
+ *
+ *   D[m, n] = act( sum_t sum_k A[m + shift[t], k] * W[n, t*K + k] + bias[n] + residual[m, n] ) * rowmask[m]
+ *
+ * A: bf16 [M_rows, K] row pitch lda (elements); rows outside [0, M_rows) read as zero.
+ * W: bf16 [N, taps*K] K-major (OIHW conv weight permuted to O,(kh,kw),I with FrozenBN scale folded in).
+ * A conv over a zero-bordered channels-last plane is this with shift[t] = (kh-1)*(W+2) + (kw-1).
+ * border != NULL zeroes output rows that are border pixels of the plane geometry (plane_h, plane_w = padded
+ * extents; rows are n*plane_h*plane_w + y*plane_w + x) so the result is again a valid zero-bordered plane.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* A; int64_t lda; int64_t M_rows;   /* rows addressable in A (TMA bound) */
+  const void* W; int64_t ldw;                   /* [N, taps*K] */
+  const float* bias;                            /* [N] fp32 or NULL */
+  const void* residual; int64_t ldr;            /* bf16 [M, N] or NULL (added before activation) */
+  void* D; int64_t ldd; int d_dtype;            /* LVCB200_BF16 or LVCB200_F32 */
+  int64_t M; int N; int K;                      /* GEMM extents (K per tap), K % 64 == 0, N % 16 == 0 */
+  int taps; int32_t shift[9];                   /* row shift per tap */
+  int relu;
+  int plane_h, plane_w;                         /* 0 = no border masking */
+} lvcb200_gemm_desc;
+
+int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d /*host*/, void* stream);
+
+/* Small memory-bound helpers of the conv engine. */
+/* (x - mean) / std, BGR planar fp32 [3,H,W] per image -> stem im2col matrix (7x7/2 pad 3) bf16
+ * [n*Hp*Wp (zero-bordered plane of the 1/2-resolution grid), Kpad] ; replaces GeneralizedRCNN.preprocess_image
+ * (lvc/modeling/meta_arch/rcnn.py:324-333) + the gather half of BasicStem.conv1 (resnet.py:588-590). */
+int lvcb200_stem_im2col(const float* const* images /*device array of n pointers*/, const int32_t* image_sizes,
+                        int n, int Hpad, int Wpad, const float* mean, const float* inv_std, void* out, int Kpad,
+                        void* stream);
+/* 3x3/2 max-pool (pad 1) between zero-bordered bf16 planes (resnet.py:591). */
+int lvcb200_maxpool3x3s2(const void* in, int n, int H, int W, int C, void* out, void* stream);
+/* stride-2 subsample of a zero-bordered plane (input side of the stride-2 1x1 convs, resnet.py:163-171, and
+ * LastLevelMaxPool p6, fpn.py:165-177). */
+int lvcb200_subsample2(const void* in, int n, int H, int W, int C, void* out, void* stream);
+/* out += nearest-2x-upsample(top)  (FPN top-down path, fpn.py:131-133), zero-bordered bf16 planes. */
+int lvcb200_upsample2_add(const void* top, int n, int Ht, int Wt, int C, void* inout, int H, int W, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVCB200_H_ */

@@ -1,0 +1,387 @@
+// Shift-GEMM on the 5th-generation tensor cores (sm_100a): tcgen05.mma with TMEM accumulators, operands
+// staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier producer/consumer pipeline, persistent CTAs.
+//
+//   D[m, n] = act( sum_t sum_k A[m + shift[t], k] * W[n, t*K + k] + bias[n] + residual[m, n] ) * rowmask[m]
+//
+// One kernel runs every dense layer of the mining path (see include/lvcb200.h): a KxK conv over a zero-bordered
+// channels-last plane is this GEMM with one row shift per tap, so the im2col matrix is never materialised --
+// TMA fetches the shifted [128 x 64] bf16 activation box straight from the plane, rows outside the tensor are
+// zero-filled by the TMA unit.  FrozenBN is folded into W / bias on the host; bias + residual + ReLU + border
+// re-zeroing are fused in the epilogue, which reads the fp32 accumulator out of TMEM (tcgen05.ld).
+//
+// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator,
+// warps 4..7 epilogue (TMEM lane quadrant = warp % 4).  Two TMEM accumulator buffers let the epilogue of tile i
+// overlap the main loop of tile i+1.  Tile = 128 x BLOCK_N, BLOCK_K = 64 (one 128-byte swizzle row).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lvcb200 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();  // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
+// start address >> 4 in bits [0,14), LBO (unused for swizzled K-major) 0, SBO = 8 rows * 128 B = 1024 >> 4 in
+// bits [32,46), version = 1 at bit 46, layout type SWIZZLE_128B = 2 in bits [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9 / 10-12 = 1), both K-major,
+// N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmParams {
+  const float* bias;
+  const __nv_bfloat16* residual; long long ldr;
+  void* D; long long ldd; int d_f32;
+  long long M; int N; int K;
+  int taps; int shift[9];
+  int relu;
+  int plane_h, plane_w;
+  int m_tiles, n_tiles, k_blocks;  // k_blocks per tap
+};
+
+template <int BLOCK_N> struct GemmCfg {
+  static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 1024 /*barriers + bias*/ + BLOCK_N * 4;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + kStages * Cfg::kStageBytesA;
+  uint8_t* ctrl = smem_al + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                 // full[kStages], empty[kStages], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * kStages + 4));
+  float* s_bias = reinterpret_cast<float*>(ctrl + 1024);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_w); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.k_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===================================== TMA producer
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
+        for (int t = 0; t < p.taps; t++) {
+          for (int kb = 0; kb < p.k_blocks; kb++, it++) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
+            tma_load_2d(smem_a0 + s * Cfg::kStageBytesA, &tmap_a, bar_full + 8 * s, kb * BLOCK_K, m0 + p.shift[t]);
+            tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * BLOCK_K, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===================================== MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      uint32_t it = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
+        const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
+        mbar_wait(bar_tempty + 8 * b, bph ^ 1u);   // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + b * BLOCK_N;
+        for (int ki = 0; ki < k_iters; ki++, it++) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * Cfg::kStageBytesA);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++)   // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);             // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(bar_tfull + 8 * b);               // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {  // ========================= epilogue warps
+    const int q = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int et = threadIdx.x - kEpiWarp0 * 32;      // 0..127
+    constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
+      const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
+      const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
+      // stage bias for this N tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long m = (long long)m0 + q * 32 + lane;
+      bool row_ok = m < p.M;
+      bool zero_row = false;
+      if (p.plane_h > 0) {
+        unsigned int plane = (unsigned)(p.plane_h * p.plane_w);
+        unsigned int rem = (unsigned int)((unsigned long long)m % plane);
+        unsigned int y = rem / (unsigned)p.plane_w, x = rem - y * (unsigned)p.plane_w;
+        zero_row = (y == 0) || (y == (unsigned)p.plane_h - 1) || (x == 0) || (x == (unsigned)p.plane_w - 1);
+      }
+      mbar_wait(bar_tfull + 8 * b, bph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += CH) {
+        uint32_t v[32];
+        if constexpr (CH == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (n0 + c >= p.N) continue;                   // uniform: whole chunk beyond N
+        float f[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
+        if (row_ok) {
+          const int ncols = (p.N - (n0 + c)) < CH ? (p.N - (n0 + c)) : CH;   // multiple of 8
+          if (p.residual != nullptr) {
+            const __nv_bfloat16* rp = p.residual + m * p.ldr + n0 + c;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              if (j < ncols) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; e++) { float2 r2 = __bfloat1622float2(h[e]); f[j + 2 * e] += r2.x; f[j + 2 * e + 1] += r2.y; }
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CH; j++) {
+            if (p.relu) f[j] = fmaxf(f[j], 0.f);
+            if (zero_row) f[j] = 0.f;
+          }
+          if (p.d_f32) {
+            float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n0 + c;
+#pragma unroll
+            for (int j = 0; j < CH; j += 4)
+              if (j < ncols) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + m * p.ldd + n0 + c;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              if (j < ncols) {
+                uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(f[j + 2 * e], f[j + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(dp + j) = u;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_encodeTiled)ptr;
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows x 64 cols], 128-byte swizzle
+static int make_tmap_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(LVCB200_EUNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return LVCB200_EINVAL;
+  }
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t s) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  gemm_bf16_tc_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tw, p);
+  return check_launch("gemm_bf16_tc_kernel");
+}
+
+}  // namespace lvcb200
+
+using namespace lvcb200;
+
+extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
+  LVC_REQUIRE(d, "gemm: NULL descriptor");
+  LVC_REQUIRE(d->M >= 0 && d->N > 0 && d->K > 0 && d->taps >= 1 && d->taps <= 9, "gemm: bad extents");
+  if (d->M == 0) return 0;
+  LVC_REQUIRE(d->A && d->W && d->D, "gemm: NULL pointer");
+  LVC_REQUIRE(d->N % 8 == 0, "gemm: N must be a multiple of 8");
+  LVC_REQUIRE(d->K % 8 == 0 && (d->taps == 1 || d->K % BLOCK_K == 0), "gemm: K must be a multiple of 8 (64 when taps > 1)");
+  LVC_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0, "gemm: lda / ldw must be multiples of 8 elements (16 bytes)");
+  LVC_REQUIRE(((uintptr_t)d->A % 16) == 0 && ((uintptr_t)d->W % 16) == 0 && ((uintptr_t)d->D % 16) == 0, "gemm: pointers must be 16-byte aligned");
+  LVC_REQUIRE(d->ldd % (d->d_dtype == LVCB200_F32 ? 4 : 8) == 0, "gemm: ldd alignment");
+  LVC_REQUIRE(!d->residual || (d->ldr % 8 == 0 && ((uintptr_t)d->residual % 16) == 0), "gemm: residual alignment");
+  LVC_REQUIRE(d->M < (1ll << 31) && d->M_rows < (1ll << 31), "gemm: M too large");
+  int bn = d->N >= 256 ? 256 : (d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16)));
+  if (d->N > 128 && d->N < 256) bn = 256;
+  GemmParams p;
+  p.bias = d->bias; p.residual = (const __nv_bfloat16*)d->residual; p.ldr = d->ldr;
+  p.D = d->D; p.ldd = d->ldd; p.d_f32 = d->d_dtype == LVCB200_F32;
+  p.M = d->M; p.N = d->N; p.K = d->K; p.taps = d->taps;
+  for (int i = 0; i < 9; i++) p.shift[i] = i < d->taps ? d->shift[i] : 0;
+  p.relu = d->relu; p.plane_h = d->plane_h; p.plane_w = d->plane_w;
+  p.m_tiles = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
+  p.n_tiles = (d->N + bn - 1) / bn;
+  p.k_blocks = (d->K + BLOCK_K - 1) / BLOCK_K;
+  CUtensorMap ta, tw;
+  int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (bn) {
+    case 256: return launch_gemm<256>(ta, tw, p, s);
+    case 128: return launch_gemm<128>(ta, tw, p, s);
+    case 64: return launch_gemm<64>(ta, tw, p, s);
+    case 32: return launch_gemm<32>(ta, tw, p, s);
+    default: return launch_gemm<16>(ta, tw, p, s);
+  }
+}

@@ -1,0 +1,304 @@
+// RPN post-processing on device, no host round trips:
+//   rpn_select_decode_kernel : per (image, level) CTA -- exact radix-select of the top-k objectness logits
+//       (same set and order as the reference's full descending sort + slice, proposal_utils.py:59-74),
+//       in-CTA sort, anchors regenerated in registers (anchor_generator.py:157-208), Box2BoxTransform.apply_deltas
+//       on the selected anchors only (box_regression.py:73-110), finite / clip / non-empty filters
+//       (proposal_utils.py:88-102).  The reference decodes all 268 569 anchors per image to keep 4 819.
+//   rpn_nms_kernel           : per (image, level) CTA -- greedy NMS (nms_core.cuh) == batched_nms(boxes, scores, lvl)
+//   rpn_merge_kernel         : per image CTA -- merge the per-level kept lists by score, first post_nms_topk.
+#include "nms_core.cuh"
+#include "sort_core.cuh"
+
+namespace lvcb200 {
+
+constexpr int kMaxTopk = 1024;
+constexpr int kMaxLevels = 8;
+
+struct RpnLevels { lvcb200_rpn_level lv[kMaxLevels]; };
+
+struct RpnWs {  // element offsets inside the workspace (per (image, level) slot of kMaxTopk entries)
+  size_t off_hdr, off_boxes, off_scores, off_valid, off_kboxes, off_kscores, off_kcount, total;
+};
+
+static RpnWs rpn_layout(int n_images, int n_levels) {
+  RpnWs w; size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o = align_up(o + b, 256); return r; };
+  size_t slots = (size_t)n_images * n_levels;
+  w.off_hdr = take(sizeof(uint32_t) * 2 * n_images);  // per image: max coordinate (ordered), valid count
+  w.off_boxes = take(slots * kMaxTopk * 16);
+  w.off_scores = take(slots * kMaxTopk * 4);
+  w.off_valid = take(slots * kMaxTopk);
+  w.off_kboxes = take(slots * kMaxTopk * 16);
+  w.off_kscores = take(slots * kMaxTopk * 4);
+  w.off_kcount = take(slots * 4);
+  w.total = o;
+  return w;
+}
+
+__device__ __forceinline__ int64_t rpn_addr(int i, int A, int W, int64_t row_stride, int64_t pix_stride, int mult) {
+  int pix = i / A, a = i - pix * A;
+  if (row_stride == 0) return (int64_t)pix * pix_stride + a * mult;
+  int y = pix / W, x = pix - y * W;
+  return (int64_t)y * row_stride + (int64_t)x * pix_stride + a * mult;
+}
+
+__global__ void __launch_bounds__(1024)
+rpn_select_decode_kernel(RpnLevels L, int n_levels, int topk, float min_box_size, float wx, float wy, float ww, float wh,
+                         const int32_t* __restrict__ image_sizes, float4* __restrict__ ws_boxes, float* __restrict__ ws_scores,
+                         unsigned char* __restrict__ ws_valid, uint32_t* __restrict__ hdr) {
+  __shared__ unsigned int hist[2048];
+  __shared__ unsigned long long sel[kMaxTopk];
+  __shared__ unsigned int warp_gt[32], warp_eq[32];
+  __shared__ unsigned int s_prefix, s_need;
+  const int img = blockIdx.x / n_levels, lvl = blockIdx.x % n_levels;
+  const lvcb200_rpn_level& lv = L.lv[lvl];
+  const int A = lv.A, W = lv.W, n = lv.H * lv.W * lv.A;
+  const int k = topk < n ? topk : n;
+  const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  // ---- exact radix select of the k-th largest key: 11 + 11 + 10 bits
+  unsigned int prefix = 0u, mask = 0u, need = (unsigned)k;
+  const int shifts[3] = {21, 10, 0};
+  const int bits[3] = {11, 11, 10};
+#pragma unroll 1
+  for (int pass = 0; pass < 3; pass++) {
+    const int sh = shifts[pass];
+    const unsigned int nb = 1u << bits[pass];
+    for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      unsigned int key = float_to_ordered(__ldg(logits + rpn_addr(i, A, W, lv.row_stride_l, lv.pix_stride_l, 1)));
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (wid == 0) {  // find the digit where the suffix count (from the top) reaches `need`
+      const int per = 2048 / 32;
+      unsigned int local = 0;
+      for (int b = 0; b < per; b++) { int bin = lane * per + b; if (bin < (int)nb) local += hist[bin]; }
+      unsigned int suffix = local;  // inclusive suffix over lanes (lane 31 is the top)
+      for (int o = 1; o < 32; o <<= 1) { unsigned int v = __shfl_down_sync(0xffffffffu, suffix, o); if (lane + o < 32) suffix += v; }
+      unsigned int above = suffix - local;  // keys in lanes above mine
+      bool mine = (above < need) && (suffix >= need);
+      if (mine) {
+        unsigned int acc = above;
+        int d = -1;
+        for (int b = per - 1; b >= 0; b--) {
+          int bin = lane * per + b;
+          unsigned int h = bin < (int)nb ? hist[bin] : 0u;
+          if (acc + h >= need) { d = bin; break; }
+          acc += h;
+        }
+        s_prefix = prefix | ((unsigned)d << sh);
+        s_need = need - acc;
+      }
+    }
+    __syncthreads();
+    prefix = s_prefix; need = s_need; mask |= (nb - 1) << sh;
+    __syncthreads();
+  }
+  const unsigned int T = prefix;  // key of the k-th largest; take all > T and the first `need` == T in index order
+
+  // ---- ordered compaction
+  for (int i = tid; i < kMaxTopk; i += blockDim.x) sel[i] = 0ull;
+  unsigned int base_gt = 0, base_eq = 0;
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    int i = i0 + tid;
+    unsigned int key = 0; bool gt = false, eq = false;
+    if (i < n) {
+      key = float_to_ordered(__ldg(logits + rpn_addr(i, A, W, lv.row_stride_l, lv.pix_stride_l, 1)));
+      gt = key > T; eq = key == T;
+    }
+    unsigned int bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) { warp_gt[wid] = __popc(bg); warp_eq[wid] = __popc(be); }
+    __syncthreads();
+    unsigned int pg = 0, pe = 0, tg = 0, te = 0;
+    for (int w2 = 0; w2 < 32; w2++) {
+      unsigned int g = warp_gt[w2], e = warp_eq[w2];
+      if (w2 < wid) { pg += g; pe += e; }
+      tg += g; te += e;
+    }
+    pg += __popc(bg & ((1u << lane) - 1u)); pe += __popc(be & ((1u << lane) - 1u));
+    unsigned int eq_before = base_eq + pe;
+    if (gt || (eq && eq_before < need)) {
+      unsigned int slot = base_gt + pg + min(eq_before, need);
+      sel[slot] = ((unsigned long long)key << 32) | (unsigned int)(~(unsigned int)i);
+    }
+    base_gt += tg; base_eq += te;
+    __syncthreads();
+  }
+  bitonic_sort_desc(sel, kMaxTopk);
+
+  // ---- decode the selected anchors
+  const int slot0 = (img * n_levels + lvl) * kMaxTopk;
+  const int ih = image_sizes[img * 2], iw = image_sizes[img * 2 + 1];
+  const float* deltas = lv.deltas + (int64_t)img * lv.img_stride_d;
+  const float clampv = 4.135166556742356f;  // log(1000/16)
+  if (tid < kMaxTopk) {
+    bool ok = false;
+    float4 bx = make_float4(0, 0, 0, 0);
+    float score = 0.f;
+    if (tid < k) {
+      unsigned long long e = sel[tid];
+      int i = (int)(~(unsigned int)(e & 0xffffffffull));
+      score = ordered_to_float((unsigned int)(e >> 32));
+      int pix = i / A, a = i - pix * A, y = pix / W, x = pix - y * W;
+      float sx = (float)(x * lv.stride), sy = (float)(y * lv.stride);
+      float ax1 = __fadd_rn(sx, lv.cell_anchors[a * 4]), ay1 = __fadd_rn(sy, lv.cell_anchors[a * 4 + 1]);
+      float ax2 = __fadd_rn(sx, lv.cell_anchors[a * 4 + 2]), ay2 = __fadd_rn(sy, lv.cell_anchors[a * 4 + 3]);
+      const float* d = deltas + rpn_addr(i, A, W, lv.row_stride_d, lv.pix_stride_d, 4);
+      float widths = __fsub_rn(ax2, ax1), heights = __fsub_rn(ay2, ay1);
+      float cx = __fadd_rn(ax1, __fmul_rn(0.5f, widths)), cy = __fadd_rn(ay1, __fmul_rn(0.5f, heights));
+      float dx = __fdiv_rn(__ldg(d), wx), dy = __fdiv_rn(__ldg(d + 1), wy);
+      float dw = fminf(__fdiv_rn(__ldg(d + 2), ww), clampv), dh = fminf(__fdiv_rn(__ldg(d + 3), wh), clampv);
+      // torch.clamp(max=) propagates NaN; fminf would drop it
+      if (__ldg(d + 2) != __ldg(d + 2)) dw = __ldg(d + 2);
+      if (__ldg(d + 3) != __ldg(d + 3)) dh = __ldg(d + 3);
+      float pcx = __fadd_rn(__fmul_rn(dx, widths), cx), pcy = __fadd_rn(__fmul_rn(dy, heights), cy);
+      float pw = __fmul_rn(expf(dw), widths), ph = __fmul_rn(expf(dh), heights);
+      float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+      float x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)), y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+      ok = isfinite(x1) && isfinite(y1) && isfinite(x2) && isfinite(y2) && isfinite(score);
+      x1 = fminf(fmaxf(x1, 0.f), (float)iw); y1 = fminf(fmaxf(y1, 0.f), (float)ih);
+      x2 = fminf(fmaxf(x2, 0.f), (float)iw); y2 = fminf(fmaxf(y2, 0.f), (float)ih);
+      ok = ok && (__fsub_rn(x2, x1) > min_box_size) && (__fsub_rn(y2, y1) > min_box_size);
+      bx = make_float4(x1, y1, x2, y2);
+    }
+    ws_boxes[slot0 + tid] = bx;
+    ws_scores[slot0 + tid] = score;
+    ws_valid[slot0 + tid] = ok ? 1 : 0;
+    // per-image max coordinate over the boxes that reach batched_nms (trick offset), and their count
+    uint32_t m = ok ? float_to_ordered(fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w))) : 0u;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    unsigned int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+    if (lane == 0 && cnt) { atomicMax(&hdr[img * 2], m); atomicAdd(&hdr[img * 2 + 1], cnt); }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rpn_nms_kernel(int n_levels, int topk, float thr, int nms_mode, const float4* __restrict__ ws_boxes,
+               const float* __restrict__ ws_scores, const unsigned char* __restrict__ ws_valid, const uint32_t* __restrict__ hdr,
+               float4* __restrict__ k_boxes, float* __restrict__ k_scores, int* __restrict__ k_count) {
+  __shared__ NmsShared sh;
+  __shared__ float kx1[kMaxTopk], ky1[kMaxTopk], kx2[kMaxTopk], ky2[kMaxTopk], kar[kMaxTopk];
+  __shared__ unsigned char flags[kMaxTopk];
+  __shared__ int warp_cnt[8];
+  const int img = blockIdx.x / n_levels, lvl = blockIdx.x % n_levels;
+  const int slot0 = blockIdx.x * kMaxTopk;
+  const int n = topk < kMaxTopk ? topk : kMaxTopk;
+  int mode = nms_mode;
+  if (mode < 0) mode = reference_cuda_nms_mode((long long)hdr[img * 2 + 1]);
+  const float off = (mode == 0) ? __fmul_rn((float)lvl, __fadd_rn(ordered_to_float(hdr[img * 2]), 1.0f)) : 0.f;
+  auto get = [&](int j, float& x1, float& y1, float& x2, float& y2) {
+    float4 b = ws_boxes[slot0 + j];
+    x1 = __fadd_rn(b.x, off); y1 = __fadd_rn(b.y, off); x2 = __fadd_rn(b.z, off); y2 = __fadd_rn(b.w, off);
+    return ws_valid[slot0 + j] != 0;
+  };
+  segment_nms(sh, get, n, thr, kx1, ky1, kx2, ky2, kar, flags);
+  __syncthreads();
+  // ordered compaction of the kept (original, un-offset) boxes
+  int base = 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    int j = j0 + threadIdx.x;
+    bool kf = j < n && flags[j];
+    unsigned int b = __ballot_sync(0xffffffffu, kf);
+    if (lane == 0) warp_cnt[wid] = __popc(b);
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w2 = 0; w2 < 8; w2++) { if (w2 < wid) pre += warp_cnt[w2]; tot += warp_cnt[w2]; }
+    if (kf) {
+      int pos = base + pre + __popc(b & ((1u << lane) - 1u));
+      k_boxes[slot0 + pos] = ws_boxes[slot0 + j];
+      k_scores[slot0 + pos] = ws_scores[slot0 + j];
+    }
+    base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) k_count[blockIdx.x] = base;
+}
+
+__global__ void __launch_bounds__(256)
+rpn_merge_kernel(int n_levels, int post_topk, const float4* __restrict__ k_boxes, const float* __restrict__ k_scores,
+                 const int* __restrict__ k_count, float4* __restrict__ proposals, float* __restrict__ prop_logits,
+                 int32_t* __restrict__ counts) {
+  const int img = blockIdx.x;
+  __shared__ int cnt[kMaxLevels];
+  if (threadIdx.x < n_levels) cnt[threadIdx.x] = k_count[img * n_levels + threadIdx.x];
+  __syncthreads();
+  int total = 0;
+  for (int l = 0; l < n_levels; l++) total += cnt[l];
+  const int out_n = total < post_topk ? total : post_topk;
+  for (int l = 0; l < n_levels; l++) {
+    const int slot = (img * n_levels + l) * kMaxTopk;
+    for (int p = threadIdx.x; p < cnt[l]; p += blockDim.x) {
+      float s = k_scores[slot + p];
+      int rank = p;
+      for (int l2 = 0; l2 < n_levels; l2++) {
+        if (l2 == l) continue;
+        const float* a = k_scores + (img * n_levels + l2) * kMaxTopk;
+        int g = count_greater_desc(a, cnt[l2], s);
+        if (l2 < l) { while (g < cnt[l2] && a[g] == s) g++; }  // ties: lower level (lower concatenated index) first
+        rank += g;
+      }
+      if (rank < post_topk) {
+        proposals[(int64_t)img * post_topk + rank] = k_boxes[slot + p];
+        prop_logits[(int64_t)img * post_topk + rank] = s;
+      }
+    }
+  }
+  for (int r = out_n + threadIdx.x; r < post_topk; r += blockDim.x) {
+    proposals[(int64_t)img * post_topk + r] = make_float4(0, 0, 0, 0);
+    prop_logits[(int64_t)img * post_topk + r] = 0.f;
+  }
+  if (threadIdx.x == 0) counts[img] = out_n;
+}
+
+}  // namespace lvcb200
+
+using namespace lvcb200;
+
+extern "C" size_t lvcb200_rpn_proposals_workspace(const lvcb200_rpn_params* p) {
+  if (!p || p->n_images <= 0 || p->n_levels <= 0) return 256;
+  return rpn_layout(p->n_images, p->n_levels).total;
+}
+
+extern "C" int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels, const lvcb200_rpn_params* p,
+                                     const int32_t* image_sizes, float* proposals, float* prop_logits, int32_t* counts,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  LVC_REQUIRE(levels && p, "rpn_proposals: NULL descriptor");
+  LVC_REQUIRE(p->n_levels >= 1 && p->n_levels <= kMaxLevels, "rpn_proposals: 1..8 levels");
+  LVC_REQUIRE(p->pre_nms_topk >= 1 && p->pre_nms_topk <= kMaxTopk, "rpn_proposals: pre_nms_topk must be in [1,1024]");
+  LVC_REQUIRE(p->post_nms_topk >= 1, "rpn_proposals: post_nms_topk must be positive");
+  if (p->n_images == 0) return 0;
+  LVC_REQUIRE(image_sizes && proposals && prop_logits && counts && workspace, "rpn_proposals: NULL pointer");
+  LVC_REQUIRE(((uintptr_t)proposals % 16) == 0, "rpn_proposals: proposals must be 16-byte aligned");
+  RpnWs w = rpn_layout(p->n_images, p->n_levels);
+  if (workspace_bytes < w.total) return set_error(LVCB200_EWORKSPACE, "rpn_proposals: workspace too small");
+  RpnLevels L;
+  for (int i = 0; i < p->n_levels; i++) {
+    L.lv[i] = levels[i];
+    LVC_REQUIRE(levels[i].A >= 1 && levels[i].A <= 3, "rpn_proposals: A must be 1..3");
+    LVC_REQUIRE(levels[i].logits && levels[i].deltas, "rpn_proposals: NULL level pointer");
+    LVC_REQUIRE((int64_t)levels[i].H * levels[i].W * levels[i].A < (1ll << 31), "rpn_proposals: level too large");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  uint32_t* hdr = (uint32_t*)(ws + w.off_hdr);
+  LVC_CUDA(cudaMemsetAsync(hdr, 0, sizeof(uint32_t) * 2 * p->n_images, s));
+  const int grid = p->n_images * p->n_levels;
+  rpn_select_decode_kernel<<<grid, 1024, 0, s>>>(L, p->n_levels, p->pre_nms_topk, p->min_box_size, p->weights[0], p->weights[1],
+                                                 p->weights[2], p->weights[3], image_sizes, (float4*)(ws + w.off_boxes),
+                                                 (float*)(ws + w.off_scores), (unsigned char*)(ws + w.off_valid), hdr);
+  int rc = check_launch("rpn_select_decode_kernel");
+  if (rc) return rc;
+  rpn_nms_kernel<<<grid, 256, 0, s>>>(p->n_levels, p->pre_nms_topk, p->nms_thresh, p->nms_mode, (const float4*)(ws + w.off_boxes),
+                                      (const float*)(ws + w.off_scores), (const unsigned char*)(ws + w.off_valid), hdr,
+                                      (float4*)(ws + w.off_kboxes), (float*)(ws + w.off_kscores), (int*)(ws + w.off_kcount));
+  rc = check_launch("rpn_nms_kernel");
+  if (rc) return rc;
+  rpn_merge_kernel<<<p->n_images, 256, 0, s>>>(p->n_levels, p->post_nms_topk, (const float4*)(ws + w.off_kboxes),
+                                               (const float*)(ws + w.off_kscores), (const int*)(ws + w.off_kcount),
+                                               (float4*)proposals, prop_logits, counts);
+  return check_launch("rpn_merge_kernel");
+}

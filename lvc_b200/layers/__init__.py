@@ -1,0 +1,5 @@
+"""Operator API mirroring detectron2/layers/__init__.py:1-13 for the ops on the mining hot path."""
+from .nms import batched_nms, nms
+from .roi_align import ROIAlign, roi_align
+
+__all__ = ["batched_nms", "nms", "ROIAlign", "roi_align"]

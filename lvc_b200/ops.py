@@ -1,0 +1,242 @@
+"""Torch-tensor front end of the fused device ops in liblvcb200.so (device memory + streams come from torch;
+the arithmetic is all in the library).  Everything here requires CUDA tensors and raises otherwise."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, OUT_NCHW, OUT_NHWC, DetParams, FMap, GemmDesc, RpnLevel, RpnParams
+
+_ws = {}
+
+
+def _workspace(tag, nbytes, device):
+    key = (tag, device.index)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise _lib.LvcB200Error(f"unsupported dtype {t.dtype}")
+
+
+# ---------------------------------------------------------------------------------------------- pooler
+def assign_boxes_to_levels(boxes, min_level=2, max_level=5, canonical_box_size=224, canonical_level=4):
+    """detectron2/modeling/poolers.py:23-59 on device.  boxes [R,4] fp32 -> int64 [R]."""
+    _lib.require_cuda(boxes)
+    b = boxes.detach().to(torch.float32).contiguous()
+    out = torch.empty(b.shape[0], dtype=torch.int64, device=b.device)
+    if b.shape[0]:
+        rc = _lib.load().lvcb200_assign_boxes_to_levels(_lib.ptr(b), b.shape[0], min_level, max_level, canonical_box_size,
+                                                        canonical_level, _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(rc, "lvcb200_assign_boxes_to_levels")
+    return out
+
+
+class Plane:
+    """A channels-last feature plane [n, H+2b, W+2b, C] (b = border, 0 or 1) viewed through lvcb200_fmap."""
+
+    def __init__(self, tensor, H, W, C, border=1, c_stride=None):
+        self.t, self.H, self.W, self.C, self.border = tensor, H, W, C, border
+        self.c_stride = c_stride or C
+        self.PH, self.PW = H + 2 * border, W + 2 * border
+
+    @property
+    def n(self):
+        return self.t.shape[0]
+
+    def fmap(self, scale):
+        es = self.t.element_size()
+        base = self.t.data_ptr() + (self.border * self.PW + self.border) * self.c_stride * es
+        return FMap(base, self.H, self.W, self.PH * self.PW, self.PW, self.c_stride, scale)
+
+    def valid(self):
+        b = self.border
+        return self.t[:, b:b + self.H, b:b + self.W, : self.C]
+
+    @staticmethod
+    def from_nchw(x, dtype=torch.bfloat16, border=1):
+        n, c, h, w = x.shape
+        t = torch.zeros((n, h + 2 * border, w + 2 * border, c), dtype=dtype, device=x.device)
+        t[:, border:border + h, border:border + w] = x.permute(0, 2, 3, 1).to(dtype)
+        return Plane(t, h, w, c, border)
+
+    def to_nchw(self):
+        return self.valid().permute(0, 3, 1, 2).float().contiguous()
+
+
+def roi_pool_fpn(planes, scales, rois, pooled=7, sampling_ratio=0, out_dtype=torch.float32, out_layout=OUT_NCHW,
+                 canonical_box_size=224, canonical_level=4, return_levels=False):
+    """ROIPooler.forward (poolers.py:191-246) in one launch.  planes: list[Plane]; rois [R,5] fp32."""
+    _lib.require_cuda(rois, *[p.t for p in planes])
+    r = rois.detach().to(torch.float32).contiguous()
+    R = r.shape[0]
+    C = planes[0].C
+    arr = (FMap * len(planes))(*[p.fmap(s) for p, s in zip(planes, scales)])
+    out = torch.empty((R, C * pooled * pooled), dtype=out_dtype, device=r.device)
+    lv = torch.empty(R, dtype=torch.int64, device=r.device) if return_levels else None
+    min_level = int(round(-math.log2(scales[0])))
+    if R:
+        rc = _lib.load().lvcb200_roi_pool_fpn(arr, len(planes), _dt(planes[0].t), C, _lib.ptr(r), R, pooled, sampling_ratio,
+                                              canonical_box_size, canonical_level, min_level, _lib.ptr(out), _dt(out), out_layout,
+                                              out.shape[1], _lib.ptr(lv), _lib.stream_ptr())
+        _lib.check(rc, "lvcb200_roi_pool_fpn")
+    if out_layout == OUT_NCHW:
+        out = out.view(R, C, pooled, pooled)
+    else:
+        out = out.view(R, pooled, pooled, C)
+    return (out, lv) if return_levels else out
+
+
+# ---------------------------------------------------------------------------------------------- RPN
+def cell_anchors(size, ratios):
+    """generate_cell_anchors (anchor_generator.py:173-208) for one size; computed in double then cast to fp32."""
+    out = []
+    area = float(size) ** 2
+    for r in ratios:
+        w = math.sqrt(area / r)
+        h = r * w
+        out += [-w / 2.0, -h / 2.0, w / 2.0, h / 2.0]
+    return out
+
+
+def rpn_proposals(level_inputs, image_sizes, anchor_sizes, anchor_ratios, strides=(4, 8, 16, 32, 64), pre_nms_topk=1000,
+                  post_nms_topk=1000, nms_thresh=0.7, min_box_size=0.0, weights=(1.0, 1.0, 1.0, 1.0), nms_mode=-1):
+    """RPN.predict_proposals on device.
+
+    level_inputs: list of dicts(logits=fp32 tensor, deltas=fp32 tensor, H, W, A, strides_l=(img,row,pix), strides_d=(img,row,pix),
+    offset_l / offset_d = element offset of (n=0,y=0,x=0,a=0)); helper `rpn_level_dense` builds one for [N,HWA] / [N,HWA,4].
+    image_sizes: int32 [N,2] device tensor (h, w).  Returns proposals [N,post,4], logits [N,post], counts [N] int32."""
+    lib = _lib.load()
+    N = image_sizes.shape[0]
+    L = len(level_inputs)
+    levels = (RpnLevel * L)()
+    keep_alive = []
+    for i, li in enumerate(level_inputs):
+        lg, dl = li["logits"], li["deltas"]
+        _lib.require_cuda(lg, dl)
+        assert lg.dtype == torch.float32 and dl.dtype == torch.float32
+        keep_alive += [lg, dl]
+        lv = levels[i]
+        lv.logits = lg.data_ptr() + 4 * li.get("offset_l", 0)
+        lv.deltas = dl.data_ptr() + 4 * li.get("offset_d", 0)
+        lv.H, lv.W, lv.A, lv.stride = li["H"], li["W"], li["A"], strides[i]
+        lv.img_stride_l, lv.row_stride_l, lv.pix_stride_l = li["strides_l"]
+        lv.img_stride_d, lv.row_stride_d, lv.pix_stride_d = li["strides_d"]
+        ca = cell_anchors(anchor_sizes[i], anchor_ratios)
+        for j, v in enumerate(ca):
+            lv.cell_anchors[j] = v
+    p = RpnParams(N, L, pre_nms_topk, post_nms_topk, nms_thresh, min_box_size, (ctypes.c_float * 4)(*weights), nms_mode)
+    dev = image_sizes.device
+    ws = _workspace("rpn", lib.lvcb200_rpn_proposals_workspace(ctypes.byref(p)), dev)
+    props = torch.empty((N, post_nms_topk, 4), dtype=torch.float32, device=dev)
+    logits = torch.empty((N, post_nms_topk), dtype=torch.float32, device=dev)
+    counts = torch.empty(N, dtype=torch.int32, device=dev)
+    rc = lib.lvcb200_rpn_proposals(levels, ctypes.byref(p), _lib.ptr(image_sizes), _lib.ptr(props), _lib.ptr(logits), _lib.ptr(counts),
+                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "lvcb200_rpn_proposals")
+    return props, logits, counts
+
+
+def rpn_level_dense(logits, deltas, H, W, A):
+    """Reference layout: logits [N, H*W*A], deltas [N, H*W*A, 4] contiguous fp32."""
+    return dict(logits=logits.contiguous(), deltas=deltas.contiguous(), H=H, W=W, A=A,
+                strides_l=(H * W * A, 0, A), strides_d=(H * W * A * 4, 0, A * 4))
+
+
+# ---------------------------------------------------------------------------------------------- detections
+def detections(cls_logits, box_deltas, proposals, roi_image, image_sizes, out_sizes, num_classes, max_rois_per_image=1000,
+               weights=(10.0, 10.0, 5.0, 5.0), score_thresh=0.05, nms_thresh=0.5, topk=100, nms_mode=-1, row_scale=None,
+               class_agnostic=False):
+    """softmax + decode + threshold + per-class NMS + top-k + detector_postprocess (fast_rcnn.py:95-137,440-493;
+    postprocessing.py:10-79) on device.  Returns boxes [N,topk,4], scores, classes (int64), rows (int64), counts (int32)."""
+    lib = _lib.load()
+    _lib.require_cuda(cls_logits, box_deltas, proposals, roi_image, image_sizes, out_sizes)
+    assert cls_logits.dtype == torch.float32 and box_deltas.dtype == torch.float32 and proposals.dtype == torch.float32
+    assert cls_logits.stride(1) == 1 and box_deltas.stride(1) == 1
+    proposals = proposals.contiguous()
+    N = image_sizes.shape[0]
+    R = cls_logits.shape[0]
+    dev = cls_logits.device
+    p = DetParams(N, num_classes, max_rois_per_image, int(class_agnostic), (ctypes.c_float * 4)(*weights), score_thresh, nms_thresh,
+                  topk, nms_mode)
+    ws = _workspace("det", lib.lvcb200_detections_workspace(ctypes.byref(p)), dev)
+    boxes = torch.empty((N, topk, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((N, topk), dtype=torch.float32, device=dev)
+    classes = torch.empty((N, topk), dtype=torch.int64, device=dev)
+    rows = torch.empty((N, topk), dtype=torch.int64, device=dev)
+    counts = torch.empty(N, dtype=torch.int32, device=dev)
+    rc = lib.lvcb200_detections(_lib.ptr(cls_logits), cls_logits.stride(0), _lib.ptr(row_scale), _lib.ptr(box_deltas),
+                                box_deltas.stride(0), _lib.ptr(proposals), _lib.ptr(roi_image), R, ctypes.byref(p),
+                                _lib.ptr(image_sizes), _lib.ptr(out_sizes), _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(classes),
+                                _lib.ptr(rows), _lib.ptr(counts), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "lvcb200_detections")
+    return boxes, scores, classes, rows, counts
+
+
+# ---------------------------------------------------------------------------------------------- kNN
+class KnnBank:
+    """Support bank after the all-gather: centred + normalised once (lvcb200_knn_prepare)."""
+
+    def __init__(self, bank, bank_cls):
+        _lib.require_cuda(bank, bank_cls)
+        lib = _lib.load()
+        self.bank = bank.detach().to(torch.float32).contiguous()
+        self.cls = bank_cls.detach().to(torch.int64).contiguous()
+        self.S, self.D = self.bank.shape
+        self.prepared = torch.empty(lib.lvcb200_knn_prepared_bytes(self.S, self.D), dtype=torch.uint8, device=bank.device)
+        rc = lib.lvcb200_knn_prepare(_lib.ptr(self.bank), self.S, self.D, _lib.ptr(self.prepared), _lib.stream_ptr())
+        _lib.check(rc, "lvcb200_knn_prepare")
+
+    def verify(self, queries, query_cls, topk=10, knn=10, return_sim=False):
+        _lib.require_cuda(queries, query_cls)
+        q = queries.detach().to(torch.float32).contiguous()
+        qc = query_cls.detach().to(torch.int64).contiguous()
+        Q = q.shape[0]
+        dev = q.device
+        top_idx = torch.empty((Q, topk), dtype=torch.int64, device=dev)
+        votes = torch.empty((Q, topk), dtype=torch.int64, device=dev)
+        keep = torch.empty(Q, dtype=torch.uint8, device=dev)
+        sim = torch.empty((Q, topk), dtype=torch.float32, device=dev) if return_sim else None
+        rc = _lib.load().lvcb200_knn_verify(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
+                                            topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep),
+                                            _lib.stream_ptr())
+        _lib.check(rc, "lvcb200_knn_verify")
+        return dict(top_idx=top_idx, votes=votes, keep=keep, top_sim=sim)
+
+
+# ---------------------------------------------------------------------------------------------- dense
+def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, relu=False, taps=1, shifts=(0,), K=None,
+         M=None, plane_hw=None):
+    """D = act(sum_t A[m+shift_t, :K] @ W[:, t*K:(t+1)*K]^T + bias + residual).  A [rows, >=K] bf16 (row pitch = stride(0)),
+    W [N, taps*K] bf16.  plane_hw=(PH, PW) zeroes border rows of a zero-bordered plane."""
+    _lib.require_cuda(A, W, bias, residual, out)
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and A.stride(1) == 1 and W.stride(1) == 1
+    N = W.shape[0]
+    K = K or (W.shape[1] // taps)
+    M = M if M is not None else A.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    assert out.stride(1) == 1
+    d = GemmDesc()
+    d.A, d.lda, d.M_rows = A.data_ptr(), A.stride(0), A.shape[0]
+    d.W, d.ldw = W.data_ptr(), W.stride(0)
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.residual, d.ldr = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
+    d.D, d.ldd, d.d_dtype = out.data_ptr(), out.stride(0), _dt(out)
+    d.M, d.N, d.K, d.taps = M, N, K, taps
+    for i, s in enumerate(shifts):
+        d.shift[i] = int(s)
+    d.relu = int(relu)
+    d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
+    rc = _lib.load().lvcb200_gemm_bf16(ctypes.byref(d), _lib.stream_ptr())
+    _lib.check(rc, "lvcb200_gemm_bf16")
+    return out

@@ -1,0 +1,92 @@
+"""tcgen05 shift-GEMM / conv engine parity (run on the B200 with -m gpu), through the C ABI.
+Floating-point kernel => the checker is a plain fp32 torch reference of the same op evaluated on the SAME bf16-rounded
+operands (fp32 accumulate); tolerance: fp32 outputs 1e-3 of the output scale (north_star's 1e-3 rel), bf16 outputs one
+bf16 rounding step (2^-8) of the output scale."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lvc_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ref_mm(a, w):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return a.float() @ w.float().t()
+
+
+def _close(got, want, bf16_out):
+    scale = float(want.abs().max()) + 1e-12
+    tol = (2.0 ** -8 if bf16_out else 1e-3) * scale
+    err = float((got.float() - want).abs().max())
+    assert err <= tol, f"max err {err:.3e} > tol {tol:.3e} (scale {scale:.3e})"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 128, 256), (1000, 1024, 1024), (257, 64, 64), (4096, 512, 2048),
+                                   (200, 416, 1024), (5000, 16, 256), (333, 32, 128), (2048, 2048, 512)])
+@pytest.mark.parametrize("f32_out", [False, True])
+def test_gemm_plain(M, N, K, f32_out):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = (torch.randn(M, K, generator=g)).bfloat16().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32 if f32_out else torch.bfloat16)
+    _close(out, _ref_mm(a, w) + bias, not f32_out)
+
+
+def test_gemm_residual_relu_and_pitches():
+    g = torch.Generator(device="cpu").manual_seed(3)
+    M, N, K = 777, 256, 192
+    abuf = torch.randn(M, K + 64, generator=g).bfloat16().to(DEV)        # A with a row pitch larger than K
+    a = abuf[:, :K]
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    res = torch.randn(M, N, generator=g).bfloat16().to(DEV)
+    dbuf = torch.full((M, N + 32), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, residual=res, relu=True, out=dbuf[:, :N])
+    _close(dbuf[:, :N], torch.relu(_ref_mm(a, w) + res.float()), True)
+    assert float((dbuf[:, N:] - 7.0).abs().max()) == 0.0                 # nothing written outside D
+    # K not a multiple of 64 (single tap): TMA zero-fills the tail of the last K block
+    a2 = torch.randn(M, 152, generator=g).bfloat16().to(DEV)
+    w2 = torch.randn(N, 152, generator=g).bfloat16().to(DEV)
+    _close(ops.gemm(a2, w2, out_dtype=torch.float32), _ref_mm(a2, w2), False)
+
+
+def _conv_weight_to_gemm(w):
+    """OIHW -> [O, (kh, kw, I)] K-major, the order of the shift-GEMM taps."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [(2, 25, 42, 128, 256), (1, 50, 84, 256, 256), (3, 13, 21, 64, 64), (2, 16, 16, 512, 512)])
+def test_conv3x3_as_shift_gemm(n, H, W, Cin, Cout):
+    g = torch.Generator(device="cpu").manual_seed(H * W)
+    x = torch.randn(n, Cin, H, W, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).bfloat16().to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    pl = ops.Plane.from_nchw(x)
+    PH, PW = H + 2, W + 2
+    shifts = [(kh - 1) * PW + (kw - 1) for kh in range(3) for kw in range(3)]
+    A = pl.t.view(-1, Cin)
+    out = ops.gemm(A, _conv_weight_to_gemm(w), bias=bias, relu=True, taps=9, shifts=shifts, K=Cin, plane_hw=(PH, PW))
+    o = ops.Plane(out.view(n, PH, PW, Cout), H, W, Cout)
+    want = torch.relu(F.conv2d(x.float(), w.float(), bias, padding=1))
+    _close(o.to_nchw(), want, True)
+    full = out.view(n, PH, PW, Cout).float()
+    assert float(full[:, 0].abs().max()) == 0 and float(full[:, -1].abs().max()) == 0        # border re-zeroed
+    assert float(full[:, :, 0].abs().max()) == 0 and float(full[:, :, -1].abs().max()) == 0
+
+
+def test_conv1x1_residual_block_tail():
+    """conv3 of a bottleneck: 1x1 conv + folded-BN bias + residual + ReLU on a bordered plane (resnet.py:195-211)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n, H, W, Cin, Cout = 2, 20, 28, 256, 1024
+    x = torch.randn(n, Cin, H, W, generator=g).bfloat16().to(DEV)
+    sc = torch.randn(n, Cout, H, W, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).bfloat16().to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    px, ps = ops.Plane.from_nchw(x), ops.Plane.from_nchw(sc)
+    out = ops.gemm(px.t.view(-1, Cin), w.view(Cout, Cin), bias=bias, residual=ps.t.view(-1, Cout), relu=True, plane_hw=(H + 2, W + 2))
+    want = torch.relu(F.conv2d(x.float(), w.float(), bias) + sc.float())
+    _close(ops.Plane(out.view(n, H + 2, W + 2, Cout), H, W, Cout).to_nchw(), want, True)

@@ -1,0 +1,267 @@
+"""Parity tests proper (run on the B200 with -m gpu): every CUDA op, called through the C ABI (ctypes), against the
+CPU oracle on the same seeded inputs and against the reference-generated golden fixtures.
+Bars: bit-exact for indices / levels / kept sets / orders; fp32 features and boxes within 1e-3 relative (stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from lvc_b200 import ops
+from lvc_b200.layers import batched_nms, nms, roi_align
+from lvc_b200.testing import coco_like_boxes, distinct_scores
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ RoIAlign
+def test_roi_align_kats():
+    x = cu(np.arange(25, dtype=np.float32).reshape(1, 1, 5, 5))
+
+    def run(roi, sr=0, aligned=True):
+        return roi_align(x, cu(np.array([roi], np.float32)), 2, 1.0, sr, aligned).flatten().tolist()
+    assert run([0, 1, 1, 3, 3]) == [6, 7, 11, 12]
+    assert run([0, 1, 1, 3, 3], aligned=False) == [9, 10, 14, 15]
+    assert run([0, 1, 1, 3, 3], sr=2) == [6, 7, 11, 12]
+    assert run([0, -10, -10, -5, -5]) == [0, 0, 0, 0]
+    assert run([0, 3, 3, 9, 9]) == [22, 0, 0, 0]
+    assert run([0, 2, 2, 2, 2]) == [0, 0, 0, 0]
+    assert run([0, 3, 3, 1, 1]) == [0, 0, 0, 0]
+    assert roi_align(x, torch.zeros((0, 5), device=DEV), 2, 1.0, 0, True).shape == (0, 1, 2, 2)
+
+
+@pytest.mark.parametrize("sr,aligned", [(0, True), (2, True), (0, False)])
+def test_roi_align_nchw_vs_oracle(sr, aligned):
+    rng = np.random.default_rng(1)
+    feat = rng.standard_normal((2, 16, 50, 84)).astype(np.float32)
+    b = coco_like_boxes(rng, 300)
+    rois = np.concatenate([rng.integers(0, 2, (300, 1)).astype(np.float32), b], 1)
+    want = O.roi_align(feat, rois, 7, 1 / 16, sr, aligned)
+    got = roi_align(cu(feat), cu(rois), 7, 1 / 16, sr, aligned).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-5)   # fp32 features: 1e-3 rel (north_star); observed ~1e-6
+
+
+def test_level_assignment_bit_exact():
+    rng = np.random.default_rng(2)
+    b = coco_like_boxes(rng, 20000)
+    sides = np.array([111.99, 112, 112.01, 223.99, 224, 224.01, 447.99, 448, 448.01, 1, 2000], np.float32)
+    kat = np.stack([np.zeros_like(sides), np.zeros_like(sides), sides, sides], 1)
+    allb = np.concatenate([b, kat])
+    got = ops.assign_boxes_to_levels(cu(allb)).cpu().numpy()
+    assert np.array_equal(got, O.assign_boxes_to_levels(allb))
+    assert (got[-11:] + 2).tolist() == [2, 3, 3, 3, 4, 4, 4, 5, 5, 2, 5]
+
+
+def _planes_from_nchw(feats, dtype):
+    return [ops.Plane.from_nchw(cu(f), dtype=dtype) for f in feats]
+
+
+def test_roi_pool_fpn_golden(golden):
+    """Fused pooler == reference ROIPooler.forward output (tests/golden/roi_pooler.npz), incl. edge-case boxes."""
+    g = golden("roi_pooler")
+    feats = [g[f"feat{i}"] for i in range(4)]
+    boxes = [g["boxes0"], g["boxes1"]]
+    rois = np.concatenate([np.concatenate([np.full((len(b), 1), i, np.float32), b], 1) for i, b in enumerate(boxes)])
+    planes = _planes_from_nchw(feats, torch.float32)
+    out, lv = ops.roi_pool_fpn(planes, (1 / 4, 1 / 8, 1 / 16, 1 / 32), cu(rois), return_levels=True)
+    assert np.array_equal(lv.cpu().numpy(), g["levels"])                       # box-to-level assignment bit-exact
+    np.testing.assert_allclose(out.cpu().numpy(), g["pooled"], rtol=1e-3, atol=1e-5)
+    # engine layout (NHWC out) carries the same numbers
+    out2 = ops.roi_pool_fpn(planes, (1 / 4, 1 / 8, 1 / 16, 1 / 32), cu(rois), out_layout=ops.OUT_NHWC)
+    np.testing.assert_array_equal(out2.permute(0, 3, 1, 2).cpu().numpy(), out.cpu().numpy())
+    # bf16 planes: inputs rounded to bf16, fp32 accumulate -> compare against the oracle on the rounded features
+    fb = [torch.from_numpy(f).bfloat16().float().numpy() for f in feats]
+    want, _ = O.roi_pooler(fb, boxes)
+    planes16 = _planes_from_nchw(feats, torch.bfloat16)
+    out3 = ops.roi_pool_fpn(planes16, (1 / 4, 1 / 8, 1 / 16, 1 / 32), cu(rois))
+    np.testing.assert_allclose(out3.cpu().numpy(), want, rtol=1e-3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def test_nms_kats():
+    b = cu(np.array([[0, 0, 10, 10], [0, 0, 10, 5]], np.float32))
+    s = cu(np.array([0.9, 0.8], np.float32))
+    assert nms(b, s, 0.5).tolist() == [0, 1]
+    assert nms(b, s, 0.49).tolist() == [0]
+    far = cu(np.array([[0, 0, 1, 1], [5, 5, 6, 6], [9, 9, 10, 10]], np.float32))
+    k = nms(far, cu(np.array([.1, .9, .5], np.float32)), 0.5)
+    assert k.dtype == torch.int64 and k.tolist() == [1, 2, 0]
+    e = nms(torch.zeros((0, 4), device=DEV), torch.zeros(0, device=DEV), 0.5)
+    assert e.dtype == torch.int64 and e.numel() == 0
+    d = cu(np.array([[3, 3, 3, 3], [3, 3, 3, 3], [0, 0, 4, 4]], np.float32))
+    assert sorted(nms(d, cu(np.array([.3, .2, .1], np.float32)), 0.5).tolist()) == [0, 1, 2]
+    same = cu(np.zeros((3, 4), np.float32) + np.array([[1, 1, 5, 5]], np.float32))
+    assert nms(same, cu(np.array([.1, .9, .5], np.float32)), 0.5).tolist() == [1]
+
+
+@pytest.mark.parametrize("tag", ["rpn900", "rpn4819", "head3000", "head900", "big41000"])
+def test_batched_nms_golden(golden, tag):
+    """Kept indices AND order identical to the reference's outputs in every regime (coordinate trick, vanilla, plain)."""
+    g = golden("batched_nms")
+    b, s, i, thr = cu(g[tag + "_boxes"]), cu(g[tag + "_scores"]), cu(g[tag + "_idxs"]), float(g[tag + "_thr"])
+    assert np.array_equal(nms(b, s, thr).cpu().numpy(), g[tag + "_keep_plain"])
+    if tag + "_keep_trick" in g:
+        assert np.array_equal(batched_nms(b, s, i, thr, mode=0).cpu().numpy(), g[tag + "_keep_trick"])
+        assert np.array_equal(batched_nms(b, s, i, thr, mode=1).cpu().numpy(), g[tag + "_keep_vanilla"])
+        # default = what the reference does on a CUDA device: trick for n <= 25000
+        assert np.array_equal(batched_nms(b, s, i, thr).cpu().numpy(), g[tag + "_keep_trick"])
+    else:
+        assert np.array_equal(batched_nms(b, s, i, thr).cpu().numpy(), g[tag + "_keep_d2cpu"])   # >= 40000: per-class loop
+
+
+def test_batched_nms_random_vs_oracle():
+    rng = np.random.default_rng(7)
+    for n, ncls, thr in ((1, 3, 0.5), (63, 2, 0.3), (64, 1, 0.7), (65, 80, 0.5), (2500, 80, 0.5), (5000, 5, 0.7), (26000, 80, 0.5)):
+        b = coco_like_boxes(rng, n)
+        s = distinct_scores(rng, n)
+        idx = rng.integers(0, ncls, n).astype(np.int64)
+        for mode in (0, 1):
+            got = batched_nms(cu(b), cu(s), cu(idx), thr, mode=mode).cpu().numpy()
+            assert np.array_equal(got, O.batched_nms(b, s, idx, thr, mode=mode)), (n, mode)
+        assert np.array_equal(batched_nms(cu(b), cu(s), cu(idx), thr).cpu().numpy(), O.batched_nms(b, s, idx, thr, device="cuda"))
+    # trick mode with negative coordinates (classes may overlap after the offset, exactly like the reference)
+    b = coco_like_boxes(rng, 800) - 300.0
+    s = distinct_scores(rng, 800)
+    idx = rng.integers(0, 4, 800).astype(np.int64)
+    assert np.array_equal(batched_nms(cu(b), cu(s), cu(idx), 0.5, mode=0).cpu().numpy(), O.batched_nms(b, s, idx, 0.5, mode=0))
+    # ties in score: set equality only (order on ties is implementation-defined in the reference)
+    s2 = np.round(s * 20) / 20
+    got = batched_nms(cu(b + 300), cu(s2), cu(idx), 0.5, mode=1).cpu().numpy()
+    assert set(got.tolist()) == set(O.batched_nms(b + 300, s2, idx, 0.5, mode=1).tolist())
+
+
+# ------------------------------------------------------------------------------------------ RPN post-processing
+def _rpn_inputs(g):
+    lv = []
+    for i in range(5):
+        h, w = (int(v) for v in g["shapes"][i])
+        lv.append(ops.rpn_level_dense(cu(g[f"logits{i}"]), cu(g[f"deltas{i}"]), h, w, 3))
+    return lv
+
+
+def test_rpn_proposals_golden(golden):
+    g = golden("rpn_postproc")
+    sizes = cu(g["image_sizes"].astype(np.int32))
+    # the golden run is the reference on CPU: 3495 candidates > 1000 -> torchvision takes the per-level (vanilla) branch
+    props, logits, counts = ops.rpn_proposals(_rpn_inputs(g), sizes, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0), nms_mode=1)
+    for n in range(2):
+        c = int(counts[n])
+        assert c == len(g[f"prop_logits{n}"])
+        assert np.array_equal(logits[n, :c].cpu().numpy(), g[f"prop_logits{n}"])          # same anchors, same order
+        np.testing.assert_allclose(props[n, :c].cpu().numpy(), g[f"prop_boxes{n}"], rtol=1e-3, atol=1e-3)
+        assert float(props[n, c:].abs().sum()) == 0.0
+
+
+def test_rpn_proposals_trick_vs_oracle(golden):
+    """The branch the reference takes on a CUDA device (<= 25000 candidates: coordinate trick), against the oracle."""
+    g = golden("rpn_postproc")
+    sizes = [tuple(int(v) for v in s) for s in g["image_sizes"]]
+    props = []
+    for i in range(5):
+        a = g[f"anchors{i}"]
+        d = g[f"deltas{i}"]
+        props.append(O.apply_deltas(d.reshape(-1, 4), np.broadcast_to(a[None], (2,) + a.shape).reshape(-1, 4), (1, 1, 1, 1)).reshape(2, -1, 4))
+    want = O.find_top_rpn_proposals(props, [g[f"logits{i}"] for i in range(5)], sizes, device="cuda")
+    got_p, got_l, counts = ops.rpn_proposals(_rpn_inputs(g), cu(g["image_sizes"].astype(np.int32)), (32, 64, 128, 256, 512), (0.5, 1.0, 2.0))
+    for n in range(2):
+        c = int(counts[n])
+        assert np.array_equal(got_l[n, :c].cpu().numpy(), want[n][1])
+        np.testing.assert_allclose(got_p[n, :c].cpu().numpy(), want[n][0], rtol=1e-3, atol=1e-3)
+
+
+def test_rpn_topk_ties_and_small_levels():
+    """All-equal logits (a zero-initialised head): selection must be the k lowest indices, deterministically."""
+    H, W, A = 9, 11, 3
+    logits = torch.zeros((1, H * W * A), device=DEV)
+    deltas = torch.zeros((1, H * W * A, 4), device=DEV)
+    sizes = cu(np.array([[64, 64]], np.int32))
+    p, l, c = ops.rpn_proposals([ops.rpn_level_dense(logits, deltas, H, W, A)], sizes, (32,), (0.5, 1.0, 2.0), strides=(8,),
+                                pre_nms_topk=50, post_nms_topk=50, nms_thresh=1.0)
+    cell = O.cell_anchors([32], (0.5, 1.0, 2.0))
+    anchors = O.clip_boxes(O.grid_anchors(cell, H, W, 8)[:50], (64, 64))
+    keep = O.nonempty(anchors)
+    assert int(c[0]) == int(keep.sum())
+    np.testing.assert_allclose(p[0, : int(c[0])].cpu().numpy(), anchors[keep], rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ box-head post-processing
+@pytest.mark.parametrize("thr", [0.05, 0.0])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_detections_vs_oracle(golden, thr, mode):
+    g = golden("fast_rcnn_inference")
+    R, K = g["logits"].shape[0], g["logits"].shape[1] - 1
+    ih, iw = (int(v) for v in g["image_shape"])
+    out_hw = (600, 1000)
+    b, s, c, r, n = ops.detections(cu(g["logits"]), cu(g["deltas"]), cu(g["props"]), torch.zeros(R, dtype=torch.int32, device=DEV),
+                                   cu(np.array([[ih, iw]], np.int32)), cu(np.array([out_hw], np.int32)), K, max_rois_per_image=R,
+                                   score_thresh=thr, nms_mode=mode)
+    probs = O.softmax_rows(g["logits"])
+    boxes = O.apply_deltas(g["deltas"], g["props"], (10, 10, 5, 5))
+    wb, wsc, wc, wr = O.fast_rcnn_inference_single_image(boxes, probs, (ih, iw), thr, 0.5, 100, nms_mode=mode)
+    wb2, keep = O.detector_postprocess(wb, (ih, iw), *out_hw)
+    n = int(n[0])
+    assert n == int(keep.sum())
+    assert np.array_equal(c[0, :n].cpu().numpy(), wc[keep]) and np.array_equal(r[0, :n].cpu().numpy(), wr[keep])
+    np.testing.assert_allclose(s[0, :n].cpu().numpy(), wsc[keep], rtol=1e-3, atol=1e-7)
+    np.testing.assert_allclose(b[0, :n].cpu().numpy(), wb2[keep], rtol=1e-3, atol=1e-3)
+
+
+def test_detections_golden_multi_image(golden):
+    """Two images in one call (second = first with rows reversed); each must reproduce the reference output."""
+    g = golden("fast_rcnn_inference")
+    R, K = g["logits"].shape[0], g["logits"].shape[1] - 1
+    ih, iw = (int(v) for v in g["image_shape"])
+    lg = np.concatenate([g["logits"], g["logits"][::-1]])
+    dl = np.concatenate([g["deltas"], g["deltas"][::-1]])
+    pr = np.concatenate([g["props"], g["props"][::-1]])
+    img = np.concatenate([np.zeros(R, np.int32), np.ones(R, np.int32)])
+    sz = np.array([[ih, iw], [ih, iw]], np.int32)
+    # reference CPU run: 1341 (t05) candidates > 1000 -> vanilla branch
+    b, s, c, r, n = ops.detections(cu(lg), cu(dl), cu(pr), cu(img), cu(sz), cu(sz), K, max_rois_per_image=R, score_thresh=0.05, nms_mode=1)
+    n0, n1 = int(n[0]), int(n[1])
+    assert n0 == len(g["t05_classes"]) == n1
+    assert np.array_equal(c[0, :n0].cpu().numpy(), g["t05_classes"]) and np.array_equal(r[0, :n0].cpu().numpy(), g["t05_rows"])
+    np.testing.assert_allclose(s[0, :n0].cpu().numpy(), g["t05_scores"], rtol=1e-3)
+    np.testing.assert_allclose(b[0, :n0].cpu().numpy(), g["t05_boxes"], rtol=1e-3, atol=1e-3)
+    assert np.array_equal(c[1, :n1].cpu().numpy(), g["t05_classes"]) and np.array_equal(r[1, :n1].cpu().numpy(), R - 1 - g["t05_rows"])
+
+
+# ------------------------------------------------------------------------------------------ kNN
+def test_knn_golden(golden):
+    g = golden("knn")
+    bank = ops.KnnBank(cu(g["bank"]), cu(g["bank_cls"]))
+    for k in (10, 5, 1):
+        r = bank.verify(cu(g["queries"]), cu(g["query_cls"]), topk=10, knn=k)
+        assert np.array_equal(np.sort(r["votes"].cpu().numpy(), 1), np.sort(g["votes"], 1))   # class multiset of the top-10
+        assert np.array_equal(r["keep"].cpu().numpy(), g[f"keep_k{k}"].astype(np.uint8))
+
+
+def test_knn_vs_oracle_tie_aware():
+    """Index parity against the scalar oracle; positions may differ only where the oracle's similarities tie to 1e-5."""
+    rng = np.random.default_rng(21)
+    S, D, Q, ncls = 600, 1024, 4000, 20
+    cls = np.repeat(np.arange(ncls), S // ncls).astype(np.int64)
+    means = (rng.standard_normal((ncls, D)) * 0.08).astype(np.float32)
+    bank = rng.standard_normal((S, D)).astype(np.float32) + means[cls] + 3.0     # large common offset: centring matters
+    qc = rng.integers(0, ncls, Q).astype(np.int64)
+    q = rng.standard_normal((Q, D)).astype(np.float32) + means[qc] + 3.0
+    want = O.knn_verify(bank, cls, q, qc)
+    got = ops.KnnBank(cu(bank), cu(cls)).verify(cu(q), cu(qc), return_sim=True)
+    gi, gs = got["top_idx"].cpu().numpy(), got["top_sim"].cpu().numpy()
+    np.testing.assert_allclose(gs, want["top_sim"], rtol=1e-3, atol=2e-6)
+    bad = gi != want["top_idx"]
+    assert bad.mean() < 1e-3
+    assert np.all(np.abs(gs[bad] - want["top_sim"][bad]) < 1e-5)      # only near-ties may swap
+    rows_bad = bad.any(1)
+    assert np.array_equal(got["keep"].cpu().numpy()[~rows_bad], want["keep"][~rows_bad])
+    # ragged / tiny inputs
+    r1 = ops.KnnBank(cu(bank[:37]), cu(cls[:37])).verify(cu(q[:5]), cu(qc[:5]), topk=10, knn=5)
+    w1 = O.knn_verify(bank[:37], cls[:37], q[:5], qc[:5], topk=10, knn=5)
+    assert np.array_equal(r1["top_idx"].cpu().numpy(), w1["top_idx"]) and np.array_equal(r1["keep"].cpu().numpy(), w1["keep"])
