@@ -131,7 +131,7 @@ int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels /*host*/, const lvcb20
  * detector_postprocess (detectron2/modeling/postprocessing.py:10-79).
  * cls_logits [R, K+1] (row pitch logit_pitch), box_deltas [R, 4K] (pitch delta_pitch) or [R,4]
  * (class_agnostic), proposals [R,4], roi_image [R] int32 image index of each row (rows grouped by image,
- * at most max_rois_per_image per image).  row_scale (optional) multiplies the logits of row r (cosine head).
+ * at most max_rois_per_image per image; -1 marks a padding row that is skipped).  row_scale (optional) multiplies the logits of row r (cosine head).
  * image_sizes [n_images,2] int32 (h,w) network input size; out_sizes [n_images,2] int32 requested output size.
  * Outputs per image, padded to topk: det_boxes [n_images, topk, 4], det_scores, det_classes (int64),
  * det_rows (int64, row index within the image), det_counts [n_images] int32.

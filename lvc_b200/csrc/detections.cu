@@ -46,6 +46,7 @@ det_score_decode_kernel(const float* __restrict__ logits, int64_t logit_pitch, c
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= R) return;
   const int img = roi_image[r];
+  if (img < 0) return;  // padded row (image produced fewer proposals than the static per-image capacity)
   const int row_in_img = (int)(r - first_row[img]);
   const float* x = logits + r * logit_pitch;
   const float sc = row_scale ? row_scale[r] : 1.0f;
@@ -243,7 +244,7 @@ det_merge_kernel(int K, int topk, const int* __restrict__ kcount, const float* _
 __global__ void det_first_row_kernel(const int32_t* __restrict__ roi_image, int64_t R, int32_t* __restrict__ first_row) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
-  if (r == 0 || roi_image[r] != roi_image[r - 1]) first_row[roi_image[r]] = (int32_t)r;
+  if (roi_image[r] >= 0 && (r == 0 || roi_image[r] != roi_image[r - 1])) first_row[roi_image[r]] = (int32_t)r;
 }
 
 }  // namespace lvcb200

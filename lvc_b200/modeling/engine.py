@@ -1,0 +1,269 @@
+"""DetectorEngine: the candidate-sourcing forward (GeneralizedRCNN.inference, lvc/modeling/meta_arch/rcnn.py:177-322)
+as a static-shape pipeline of liblvcb200 launches over zero-bordered channels-last bf16 planes.
+
+    preprocess+stem gather -> 7x7 stem GEMM -> maxpool -> 33/16 bottlenecks (1x1 / 3x3(9 shifted taps) / 1x1+residual GEMMs)
+    -> FPN (lateral GEMM, upsample-add, 3x3 GEMM, p6 subsample) -> RPN head (3x3 GEMM, fused 1x1 logits|deltas GEMM)
+    -> top-k select + decode + NMS + merge -> fused multi-level RoIAlign -> fc1 / fc2 / fused predictor GEMMs
+    -> softmax + decode + per-class NMS + top-k + postprocess
+
+Every arithmetic step is a kernel of liblvcb200.so; torch provides device buffers, the stream and (optionally) CUDA-graph
+capture of the whole sequence.  Weights come from a state dict with the reference's names; FrozenBN
+(batch_norm.py:45-65) is folded into the conv weights / bias in fp32 before the bf16 cast.
+"""
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _lib, ops
+from ..config import DetectorConfig
+
+STRIDES = (4, 8, 16, 32, 64)
+
+
+def _fold_bn(sd, prefix, eps=1e-5):
+    w = sd[prefix + ".weight"].float()
+    if prefix + ".norm.weight" in sd:
+        scale = sd[prefix + ".norm.weight"].float() * (sd[prefix + ".norm.running_var"].float() + eps).rsqrt()
+        bias = sd[prefix + ".norm.bias"].float() - sd[prefix + ".norm.running_mean"].float() * scale
+        w = w * scale.view(-1, 1, 1, 1)
+    else:
+        b = sd.get(prefix + ".bias")
+        bias = b.float() if b is not None else torch.zeros(w.shape[0])
+    return w, bias
+
+
+def _to_gemm_weight(w):
+    """OIHW -> [O, (kh, kw, I)]: tap-major K, matching the row-shift order of the shift-GEMM."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+class _Conv:
+    def __init__(self, sd, prefix, device, relu):
+        w, b = _fold_bn(sd, prefix)
+        self.cout, self.cin, self.k, _ = w.shape
+        self.w = _to_gemm_weight(w).to(device=device, dtype=torch.bfloat16)
+        self.b = b.to(device)
+        self.relu = relu
+
+
+class DetectorEngine:
+    def __init__(self, cfg: DetectorConfig, state_dict: Dict[str, torch.Tensor], device="cuda", use_cuda_graph=False):
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.LvcB200Error("DetectorEngine needs a CUDA device (no CPU fallback)")
+        self.cfg, self.device = cfg, torch.device(device)
+        self.use_cuda_graph = use_cuda_graph
+        sd = state_dict
+        dev = self.device
+        bu = "backbone.bottom_up."
+        # stem: K = 147 padded to 192 (3 K-blocks of 64)
+        w, b = _fold_bn(sd, bu + "stem.conv1")
+        ws = torch.zeros(64, 192)
+        ws[:, :147] = w.reshape(64, 147)
+        self.stem_w, self.stem_b = ws.to(dev, torch.bfloat16), b.to(dev)
+        self.blocks = []
+        for si, nblocks in enumerate(cfg.blocks_per_stage):
+            stage = si + 2
+            for bi in range(nblocks):
+                p = f"{bu}res{stage}.{bi}."
+                blk = dict(stage=stage, stride=2 if (bi == 0 and stage > 2) else 1,
+                           conv1=_Conv(sd, p + "conv1", dev, True), conv2=_Conv(sd, p + "conv2", dev, True),
+                           conv3=_Conv(sd, p + "conv3", dev, True),
+                           shortcut=_Conv(sd, p + "shortcut", dev, False) if (p + "shortcut.weight") in sd else None,
+                           last=bi == nblocks - 1)
+                self.blocks.append(blk)
+        self.lateral = {l: _Conv(sd, f"backbone.fpn_lateral{l}", dev, False) for l in (2, 3, 4, 5)}
+        self.fpn_out = {l: _Conv(sd, f"backbone.fpn_output{l}", dev, False) for l in (2, 3, 4, 5)}
+        rp = "proposal_generator.rpn_head."
+        self.rpn_conv = _Conv(sd, rp + "conv", dev, True)
+        A = len(cfg.anchor_ratios)
+        self.A = A
+        wh = torch.zeros(16, 256)
+        bh = torch.zeros(16)
+        wh[:A] = sd[rp + "objectness_logits.weight"].float().view(A, 256)
+        wh[A:A + 4 * A] = sd[rp + "anchor_deltas.weight"].float().view(4 * A, 256)
+        bh[:A] = sd[rp + "objectness_logits.bias"].float()
+        bh[A:A + 4 * A] = sd[rp + "anchor_deltas.bias"].float()
+        self.rpn_head_w, self.rpn_head_b = wh.to(dev, torch.bfloat16), bh.to(dev)
+        # box head: fc1 input index c*49+h*7+w (box_head.py:86-87) -> permuted to the pooler's (h, w, c) order
+        res = cfg.pooler_resolution
+        self.fcs = []
+        for i in range(cfg.num_fc):
+            w = sd[f"roi_heads.box_head.fc{i + 1}.weight"].float()
+            if i == 0:
+                w = w.view(-1, 256, res, res).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+            self.fcs.append((w.contiguous().to(dev, torch.bfloat16), sd[f"roi_heads.box_head.fc{i + 1}.bias"].float().to(dev)))
+        K = cfg.num_classes
+        self.cls_cols = (K + 1 + 15) // 16 * 16
+        wc = sd["roi_heads.box_predictor.cls_score.weight"].float()
+        self.cosine = cfg.output_layer == "CosineSimOutputLayers"
+        if self.cosine:  # fast_rcnn.py:830-837 (first forward of a freshly loaded model)
+            wc = wc / (wc.norm(p=2, dim=1, keepdim=True) + 1e-5)
+        wb = sd["roi_heads.box_predictor.bbox_pred.weight"].float()
+        wp = torch.zeros(self.cls_cols + 4 * K, wc.shape[1])
+        bp = torch.zeros(self.cls_cols + 4 * K)
+        wp[:K + 1] = wc
+        wp[self.cls_cols:] = wb
+        if not self.cosine:
+            bp[:K + 1] = sd["roi_heads.box_predictor.cls_score.bias"].float()
+        bp[self.cls_cols:] = sd["roi_heads.box_predictor.bbox_pred.bias"].float()
+        self.pred_w, self.pred_b = wp.to(dev, torch.bfloat16), bp.to(dev)
+        self.mean = torch.tensor(cfg.pixel_mean, dtype=torch.float32, device=dev)
+        self.inv_std = (1.0 / torch.tensor(cfg.pixel_std, dtype=torch.float32)).to(dev)
+        self._bufs = {}
+        self._graphs = {}
+        self.debug = None  # set to a dict to capture intermediates (tests)
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name, shape, dtype=torch.bfloat16, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _plane(self, name, n, H, W, C, dtype=torch.bfloat16):
+        return ops.Plane(self._buf(name, (n, H + 2, W + 2, C), dtype), H, W, C)
+
+    # ------------------------------------------------------------------ layers
+    def _conv(self, name, x: ops.Plane, conv: _Conv, residual: Optional[ops.Plane] = None, out_dtype=torch.bfloat16):
+        n = x.n
+        out = self._plane(name, n, x.H, x.W, conv.cout, out_dtype)
+        PW = x.PW
+        if conv.k == 3:
+            shifts = [(kh - 1) * PW + (kw - 1) for kh in range(3) for kw in range(3)]
+            taps = 9
+        else:
+            shifts, taps = (0,), 1
+        ops.gemm(x.t.view(-1, x.C), conv.w, bias=conv.b, residual=residual.t.view(-1, conv.cout) if residual is not None else None,
+                 out=out.t.view(-1, conv.cout), relu=conv.relu, taps=taps, shifts=shifts, K=conv.cin, plane_hw=(x.PH, x.PW))
+        return out
+
+    def _subsample(self, name, x: ops.Plane):
+        Ho, Wo = (x.H - 1) // 2 + 1, (x.W - 1) // 2 + 1
+        out = self._plane(name, x.n, Ho, Wo, x.C)
+        _lib.check(_lib.load().lvcb200_subsample2(_lib.ptr(x.t), x.n, x.H, x.W, x.C, _lib.ptr(out.t), _lib.stream_ptr()), "subsample2")
+        return out
+
+    # ------------------------------------------------------------------ forward pieces
+    def backbone(self, img_ptrs, sizes_dev, n, Hpad, Wpad):
+        lib = _lib.load()
+        Ho, Wo = Hpad // 2, Wpad // 2
+        col = self._buf("stem_col", (n * (Ho + 2) * (Wo + 2), 192))
+        _lib.check(lib.lvcb200_stem_im2col(_lib.ptr(img_ptrs), _lib.ptr(sizes_dev), n, Hpad, Wpad, _lib.ptr(self.mean),
+                                           _lib.ptr(self.inv_std), _lib.ptr(col), 192, _lib.stream_ptr()), "stem_im2col")
+        stem = self._plane("stem", n, Ho, Wo, 64)
+        ops.gemm(col, self.stem_w, bias=self.stem_b, out=stem.t.view(-1, 64), relu=True, K=192, plane_hw=(Ho + 2, Wo + 2))
+        x = self._plane("pool", n, Ho // 2, Wo // 2, 64)
+        _lib.check(lib.lvcb200_maxpool3x3s2(_lib.ptr(stem.t), n, Ho, Wo, 64, _lib.ptr(x.t), _lib.stream_ptr()), "maxpool")
+        feats = {}
+        for i, blk in enumerate(self.blocks):
+            tag = f"b{i}"
+            xin = self._subsample(tag + "_sub", x) if blk["stride"] == 2 else x
+            o1 = self._conv(tag + "_c1", xin, blk["conv1"])
+            o2 = self._conv(tag + "_c2", o1, blk["conv2"])
+            sc = self._conv(tag + "_sc", xin, blk["shortcut"]) if blk["shortcut"] is not None else x
+            x = self._conv(tag + "_c3", o2, blk["conv3"], residual=sc)
+            if blk["last"]:
+                feats[blk["stage"]] = x
+        return feats
+
+    def fpn(self, feats):
+        lib = _lib.load()
+        out = {}
+        prev = None
+        for l in (5, 4, 3, 2):
+            lat = self._conv(f"lat{l}", feats[l], self.lateral[l])
+            if prev is not None:
+                _lib.check(lib.lvcb200_upsample2_add(_lib.ptr(prev.t), prev.n, prev.H, prev.W, 256, _lib.ptr(lat.t), lat.H, lat.W,
+                                                     _lib.stream_ptr()), "upsample2_add")
+            prev = lat
+            out[l] = self._conv(f"p{l}", lat, self.fpn_out[l])
+        out[6] = self._subsample("p6", out[5])
+        return out
+
+    def rpn(self, pyramid, sizes_dev):
+        cfg = self.cfg
+        levels = []
+        for l in (2, 3, 4, 5, 6):
+            p = pyramid[l]
+            t = self._conv(f"rpn_t{l}", p, self.rpn_conv)
+            head = self._buf(f"rpn_h{l}", (p.n * p.PH * p.PW, 16), torch.float32)
+            ops.gemm(t.t.view(-1, 256), self.rpn_head_w, bias=self.rpn_head_b, out=head, K=256)
+            off = (p.PW + 1) * 16
+            levels.append(dict(logits=head, deltas=head, H=p.H, W=p.W, A=self.A, offset_l=off, offset_d=off + self.A,
+                               strides_l=(p.PH * p.PW * 16, p.PW * 16, 16), strides_d=(p.PH * p.PW * 16, p.PW * 16, 16)))
+        return ops.rpn_proposals(levels, sizes_dev, cfg.anchor_sizes, cfg.anchor_ratios, STRIDES, cfg.rpn_pre_nms_topk,
+                                 cfg.rpn_post_nms_topk, cfg.rpn_nms_thresh, cfg.rpn_min_box_size, cfg.rpn_bbox_weights)
+
+    def roi_heads(self, pyramid, props, counts, sizes_dev, out_sizes_dev):
+        cfg = self.cfg
+        n, P = props.shape[0], props.shape[1]
+        ar = torch.arange(P, device=self.device)
+        valid = ar[None, :] < counts[:, None]
+        img_col = torch.arange(n, device=self.device, dtype=torch.float32)[:, None, None].expand(n, P, 1)
+        rois = torch.cat([img_col, props], dim=2).view(n * P, 5)
+        roi_image = torch.where(valid, torch.arange(n, device=self.device, dtype=torch.int32)[:, None], -1).to(torch.int32).reshape(-1)
+        planes = [pyramid[l] for l in (2, 3, 4, 5)]
+        pooled = ops.roi_pool_fpn(planes, [1.0 / s for s in STRIDES[:4]], rois, cfg.pooler_resolution, cfg.pooler_sampling_ratio,
+                                  out_dtype=torch.bfloat16, out_layout=ops.OUT_NHWC)
+        x = pooled.view(n * P, -1)
+        for i, (w, b) in enumerate(self.fcs):
+            x = ops.gemm(x, w, bias=b, relu=True, out=self._buf(f"fc{i}", (n * P, w.shape[0])))
+        pred = ops.gemm(x, self.pred_w, bias=self.pred_b, out=self._buf("pred", (n * P, self.pred_w.shape[0]), torch.float32))
+        row_scale = None
+        if self.cosine:  # scores = scale * (x / (|x| + 1e-5)) . w_hat   (fast_rcnn.py:826-840)
+            row_scale = cfg.cosine_scale / (x.float().norm(p=2, dim=1) + 1e-5)
+        K = cfg.num_classes
+        if self.debug is not None:
+            self.debug.update(pooled=pooled, head=x, pred=pred, rois=rois, roi_image=roi_image)
+        return ops.detections(pred[:, : K + 1], pred[:, self.cls_cols:], props.view(-1, 4), roi_image, sizes_dev, out_sizes_dev, K,
+                              max_rois_per_image=P, weights=cfg.roi_bbox_weights, score_thresh=cfg.score_thresh_test,
+                              nms_thresh=cfg.nms_thresh_test, topk=cfg.detections_per_image, row_scale=row_scale)
+
+    # ------------------------------------------------------------------ whole forward on device-resident inputs
+    def forward_device(self, img_ptrs, sizes_dev, out_sizes_dev, n, Hpad, Wpad):
+        feats = self.backbone(img_ptrs, sizes_dev, n, Hpad, Wpad)
+        pyramid = self.fpn(feats)
+        props, plogits, counts = self.rpn(pyramid, sizes_dev)
+        if self.debug is not None:
+            self.debug.update(feats=feats, pyramid=pyramid, props=props, prop_logits=plogits, prop_counts=counts)
+        return self.roi_heads(pyramid, props, counts, sizes_dev, out_sizes_dev)
+
+    def run(self, images: List[torch.Tensor], out_sizes=None):
+        """images: list of fp32 [3,H,W] CUDA tensors (BGR, 0..255).  Returns (boxes [n,100,4], scores, classes, rows, counts)."""
+        _lib.require_cuda(*images)
+        cfg = self.cfg
+        n = len(images)
+        images = [im.contiguous().float() for im in images]
+        sizes = [tuple(im.shape[-2:]) for im in images]
+        d = cfg.size_divisibility
+        Hpad = (max(s[0] for s in sizes) + d - 1) // d * d
+        Wpad = (max(s[1] for s in sizes) + d - 1) // d * d
+        out_sizes = out_sizes or sizes
+        key = (n, Hpad, Wpad)
+        st = self._graphs.get(key)
+        if st is None:
+            st = dict(ptrs=torch.zeros(n, dtype=torch.int64, device=self.device),
+                      sizes=torch.zeros((n, 2), dtype=torch.int32, device=self.device),
+                      outs=torch.zeros((n, 2), dtype=torch.int32, device=self.device), graph=None, result=None, warm=0)
+            self._graphs[key] = st
+        st["ptrs"].copy_(torch.tensor([im.data_ptr() for im in images], dtype=torch.int64), non_blocking=False)
+        st["sizes"].copy_(torch.tensor(sizes, dtype=torch.int32))
+        st["outs"].copy_(torch.tensor(out_sizes, dtype=torch.int32))
+        self._keepalive = images
+        if not self.use_cuda_graph or self.debug is not None:
+            return self.forward_device(st["ptrs"], st["sizes"], st["outs"], n, Hpad, Wpad)
+        if st["graph"] is None:
+            if st["warm"] < 1:   # first call eager: allocates every buffer, sets kernel attributes
+                st["warm"] += 1
+                return self.forward_device(st["ptrs"], st["sizes"], st["outs"], n, Hpad, Wpad)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                st["result"] = self.forward_device(st["ptrs"], st["sizes"], st["outs"], n, Hpad, Wpad)
+            st["graph"] = g
+        st["graph"].replay()
+        return st["result"]
