@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- pseudo-label mining throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (default)
+    python bench.py --impl reference --steps 2 --warmup 1    # the reference's CPU path (oracle port) on the host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of 8 synthetic 3x800x1333 images per GPU (BASELINE.json configs[1]:
+Faster R-CNN R101-FPN inference, batch 8, random-init weights) -- backbone + FPN + RPN + proposals + RoIAlign + box head +
+per-class NMS + top-100 + postprocess.  Images shard across ranks with no data-path collective (weak scaling).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 8
+H, W = 800, 1333
+METRIC = "pseudo-label images/sec (1333x800)"
+
+
+def make_images(seed0, n, device=None, pin=False):
+    ims = []
+    for i in range(n):
+        g = torch.Generator().manual_seed(seed0 + i)
+        im = torch.rand(3, H, W, generator=g) * 255
+        if pin and torch.cuda.is_available():
+            im = im.pin_memory()
+        ims.append(im.to(device) if device is not None else im)
+    return ims
+
+
+def bench_cfg():
+    from lvc_b200.config import DetectorConfig
+    # candidate-sourcing model (faster_rcnn_R_50_FPN_ft_all_30shot_aug_ftmore_dropout.yaml with RESNETS.DEPTH 101)
+    return DetectorConfig(depth=101, output_layer="CosineSimOutputLayers", score_thresh_test=0.05)
+
+
+def algorithmic_gflop_per_image(cfg, n_props=1000):
+    """2*MACs of every conv / FC on the path at 800x1344 (valid pixels only), SURVEY.md 8(d)."""
+    Hp, Wp = 800, 1344
+    mac = 0.0
+    h, w = Hp // 2, Wp // 2
+    mac += h * w * 64 * 147
+    h, w = h // 2, w // 2
+    cin = 64
+    for si, nb in enumerate(cfg.blocks_per_stage):
+        bott, cout = 64 * 2 ** si, 256 * 2 ** si
+        for b in range(nb):
+            if b == 0 and si > 0:
+                h, w = h // 2, w // 2
+            if b == 0:
+                mac += h * w * cin * cout
+            mac += h * w * (cin * bott + bott * bott * 9 + bott * cout)
+            cin = cout
+    sizes = [(200, 336), (100, 168), (50, 84), (25, 42), (13, 21)]
+    for (hh, ww), c in zip(sizes[:4], (256, 512, 1024, 2048)):
+        mac += hh * ww * (c * 256 + 256 * 256 * 9)
+    for hh, ww in sizes:
+        mac += hh * ww * (256 * 256 * 9 + 256 * 15)
+    d = 256 * 49
+    for _ in range(cfg.num_fc):
+        mac += n_props * d * cfg.fc_dim
+        d = cfg.fc_dim
+    mac += n_props * d * (cfg.num_classes + 1 + 4 * cfg.num_classes)
+    return 2 * mac / 1e9
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nme, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1401.3), d.get("hbm_gbs", 6536.4), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+def cpu_baseline(cfg, sd, n_images=2):
+    """The reference's CPU path restated by the oracle (fp32, torch CPU kernels + C oracle), all host threads."""
+    from oracle import model as OM
+    torch.set_num_threads(os.cpu_count())
+    ims = make_images(0, n_images)
+    OM.detector_forward(cfg, sd, ims[:1], device="cpu")  # warm-up
+    t = time.time()
+    for im in ims:
+        OM.detector_forward(cfg, sd, [im], device="cpu")
+    dt = time.time() - t
+    return {"value": n_images / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_images} images of the same 3x800x1333 R101-FPN workload, batch 1 as in the reference's test loader"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Python and cannot travel to
+    the GPU box (no /root/reference there), so this times the oracle port (oracle/model.py) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from lvc_b200.weights import synthetic_state_dict
+    from oracle import model as OM
+    cfg = bench_cfg()
+    sd = synthetic_state_dict(cfg, 0)
+    torch.set_num_threads(os.cpu_count())
+    ims = make_images(0, 1)
+    for _ in range(args.warmup):
+        OM.detector_forward(cfg, sd, ims, device="cpu")
+    t = time.time()
+    for _ in range(args.steps):
+        OM.detector_forward(cfg, sd, ims, device="cpu")
+    dt = time.time() - t
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Faster R-CNN R101-FPN (CosineSim head) inference, synthetic 3x800x1333, random-init weights",
+                       "images_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "1 image per step (batch 1, as the reference's test loader), host cores only"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from lvc_b200 import _lib, ops
+    from lvc_b200.modeling import GeneralizedRCNN
+    from lvc_b200.weights import synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(args.warmup, 3)
+    K = args.steps
+
+    cfg = bench_cfg()
+    sd = synthetic_state_dict(cfg, 0)
+    model = GeneralizedRCNN(cfg, sd, dev, use_cuda_graph=not args.no_graph)
+    eng = model.engine
+    # rank r processes its own contiguous block of the synthetic image stream (InferenceSampler rule)
+    seed0 = rank * BATCH
+    dev_images = make_images(seed0, BATCH, device=dev)
+    host_images = make_images(seed0, BATCH, pin=True)
+    batched = [{"image": im, "height": H, "width": W} for im in host_images]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    launches0 = _lib.launch_count()
+    eng.run(dev_images)          # eager: allocates buffers; counts launches of one step
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - launches0
+    for _ in range(W_):
+        out = eng.run(dev_images)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = eng.run(dev_images)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    n_det = int(out[4].sum())
+
+    # ---------------- end to end through the public API, host buffers (`e2e`)
+    for _ in range(2):
+        res = model(batched)
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        res = model(batched)
+    f1.record()
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
+    sampler.stop_flag = True
+    h2d = sum(im.numel() * im.element_size() for im in host_images)
+    d2h = BATCH * (cfg.detections_per_image * 6 + 1) * 4
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---------------- roofline of the dominant kernel (tcgen05 shift-GEMM): per-launch CUDA events, eager pass
+    roof = None
+    if rank == 0:
+        peak_tf, peak_hbm, which = measured_peaks()
+        ops.GEMM_EVENTS = []
+        use_graph, eng.use_cuda_graph = eng.use_cuda_graph, False
+        for _ in range(2):
+            ops.GEMM_EVENTS.clear()
+            eng.run(dev_images)
+        torch.cuda.synchronize()
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.GEMM_EVENTS)
+        n_gemm = len(ops.GEMM_EVENTS)
+        ops.GEMM_EVENTS = None
+        eng.use_cuda_graph = use_graph
+        alg_tflop = algorithmic_gflop_per_image(cfg) * BATCH / 1e3
+        ach = alg_tflop / (gemm_ms / 1e3)
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all dense layers: 104 backbone convs, FPN, RPN head, box head)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": f"{which} (sustained bf16, MEASURED_PEAKS.json)", "launches": n_gemm,
+                "avg_launch_ms": gemm_ms / max(n_gemm, 1), "gemm_ms_per_step": gemm_ms, "algorithmic_tflop_per_step": alg_tflop,
+                "gemm_share_of_step": gemm_ms / (ms / K)}
+
+    if rank == 0:
+        imgs = world * BATCH * K
+        line = {"metric": METRIC, "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "Faster R-CNN R101-FPN (CosineSim head) inference, batch 8 synthetic 3x800x1333 per GPU, "
+                                       "random-init weights (conv3 BN gamma 0.2), SCORE_THRESH_TEST 0.05",
+                           "images_per_step_per_gpu": BATCH, "parallelism": f"dp{world} (images sharded, no data-path collective)",
+                           "l2_policy": "no flush: every step streams several GB of activations (>> 126 MB L2); inputs 102 MB/step",
+                           "cuda_graph": bool(eng.use_cuda_graph), "detections_last_step": n_det},
+                "clocks": sampler.summary(),
+                "e2e": {"value": imgs / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / K,
+                        "api": "lvc_b200.modeling.GeneralizedRCNN(batched_inputs) with pinned host fp32 images"},
+                "gpu_launches": launches_per_step * K,
+                "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, sd)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""Host-side mirror of the label-verification step of tools/run_nearest_neighbours.py:
+
+    assemble_tensors (:131-139), the support-bank all-gather (:303-309), run_nearest_neighbours (:142-162),
+    get_nn_class_confirmatory (:214-227)
+
+with the same names, argument meaning and in-place mutation of the per-image ``Instances`` (fields ``crop_feats``,
+``gt_classes`` in; ``top10_shots``, ``keep`` out).  The arithmetic runs in liblvcb200's kNN kernels: all images'
+queries are batched into ONE device call instead of a per-image CPU broadcast.  The reference gathers pickled python
+objects over gloo; here the bank shard is a device tensor all-gathered by torch.distributed (NCCL over NVLink on GPUs,
+gloo in the CPU tests), uneven shards handled by a size exchange + padding.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def assemble_tensors(shot_features: List[dict]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tools/run_nearest_neighbours.py:131-139: concatenate and sort the support descriptors by class."""
+    classes = torch.cat([x["instances"].gt_classes for x in shot_features])
+    sorter = classes.argsort()
+    desc = torch.cat([x["instances"].crop_feats for x in shot_features])
+    return classes[sorter], desc[sorter]
+
+
+def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None):
+    """The ONE exchange step of the path (run_nearest_neighbours.py:303-309): every rank ends with the full bank,
+    rank-major order (== torch.cat(comm.all_gather(...)))."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return shot_classes, shot_descriptors
+    world = dist.get_world_size(group)
+    dev = shot_descriptors.device
+    n = torch.tensor([shot_descriptors.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx, D = max(sizes), shot_descriptors.shape[1]
+    # one padded buffer carries descriptors and (bit-cast) classes: a single collective on the data path
+    pack = torch.zeros((mx, D + 2), dtype=torch.float32, device=dev)
+    pack[: sizes[dist.get_rank(group)], :D] = shot_descriptors.float()
+    pack[: sizes[dist.get_rank(group)], D:] = shot_classes.to(torch.int64).view(-1, 1).view(torch.float32).view(-1, 2) \
+        if shot_classes.numel() else pack[:0, D:]
+    out = torch.empty((world, mx, D + 2), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(out.view(world * mx, D + 2), pack, group=group) if dev.type == "cuda" else \
+        dist.all_gather(list(out.unbind(0)), pack, group=group)
+    desc = torch.cat([out[r, : sizes[r], :D] for r in range(world)])
+    cls = torch.cat([out[r, : sizes[r], D:].contiguous().view(torch.int64).view(-1) for r in range(world)])
+    return cls, desc
+
+
+def run_nearest_neighbours(shot_classes, shot_descriptors, query_features: List[dict], cosine: bool = True,
+                           device: Optional[torch.device] = None, topk: int = 10):
+    """tools/run_nearest_neighbours.py:142-162.  Sets ``top10_shots`` ([Qi, 10] int64 class votes, best first) on every
+    image's ``Instances`` and returns the list, like the reference."""
+    if not cosine:
+        raise NotImplementedError("QUERY_EXPAND.COSINE_SIM=False (negative-cdist ranking) is not on the B200 path")
+    if not query_features:
+        return query_features
+    device = device or (shot_descriptors.device if shot_descriptors.is_cuda else torch.device("cuda"))
+    bank = ops.KnnBank(shot_descriptors.to(device), shot_classes.to(device))
+    counts = [len(d["instances"].get("crop_feats")) for d in query_features]
+    feats = torch.cat([d["instances"].get("crop_feats") for d in query_features]).to(device)
+    dt = [d["instances"].gt_classes if d["instances"].has("gt_classes") else torch.zeros(c, dtype=torch.int64)
+          for d, c in zip(query_features, counts)]
+    qcls = torch.cat(dt).to(device)
+    res = bank.verify(feats, qcls, topk=topk, knn=topk)
+    votes = res["votes"].cpu()
+    idx = res["top_idx"].cpu()
+    off = 0
+    for d, c in zip(query_features, counts):
+        d["instances"].set("top10_shots", votes[off:off + c])
+        d["instances"].set("top10_idx", idx[off:off + c])
+        off += c
+    return query_features
+
+
+def get_nn_class_confirmatory(query_features: List[dict], k: int):
+    """tools/run_nearest_neighbours.py:214-227: keep = (mode of the first k votes == detector class).
+    torch.mode returns the smallest most-frequent value; the same rule is applied here on the stored votes."""
+    for d in query_features:
+        inst = d["instances"]
+        votes = inst.get("top10_shots")[:, :k]
+        dt = inst.gt_classes
+        keep = torch.zeros(len(inst), dtype=torch.int64)
+        if len(inst):
+            # mode with smallest-value tie-break, vectorised: count matches per position, pick max count then min value
+            eq = (votes[:, :, None] == votes[:, None, :]).sum(-1)            # [Q, k] multiplicity of each vote
+            best = eq.max(dim=1, keepdim=True).values
+            cand = torch.where(eq == best, votes, torch.full_like(votes, torch.iinfo(torch.int64).max))
+            nn_class = cand.min(dim=1).values
+            keep = (nn_class == dt.to(nn_class.device)).long()
+        inst.set("keep", keep)

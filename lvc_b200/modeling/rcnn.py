@@ -1,0 +1,59 @@
+"""Host-side mirror of the reference's model-level interface for candidate sourcing:
+``GeneralizedRCNN`` (lvc/modeling/meta_arch/rcnn.py:25-333).  Same call contract --
+
+    model(batched_inputs: list[dict(image: Tensor[3,H,W] (BGR, 0..255), height, width, ...)])
+        -> list[dict("instances": Instances(pred_boxes: Boxes, scores, pred_classes))]
+
+-- so that ``inference_on_dataset`` (lvc/evaluation/evaluator.py:117-126) can drive it unchanged; the arithmetic is the
+DetectorEngine's liblvcb200 launches.  Inference only (``model.training`` is always False): the training branches of the
+reference are out of scope."""
+from typing import Dict, List
+
+import torch
+
+from ..config import DetectorConfig
+from ..structures import Boxes, Instances
+from .engine import DetectorEngine
+
+
+class GeneralizedRCNN:
+    def __init__(self, cfg: DetectorConfig, state_dict: Dict[str, torch.Tensor], device="cuda", use_cuda_graph=True):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.engine = DetectorEngine(cfg, state_dict, device, use_cuda_graph=use_cuda_graph)
+        self.training = False
+
+    def eval(self):
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("lvc_b200.GeneralizedRCNN is inference-only (pseudo-label mining path)")
+        return self
+
+    def to_device(self, batched_inputs):
+        """H2D of the batch (rcnn.py:328): uint8 or float images, pinned sources copy asynchronously."""
+        return [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+
+    @torch.no_grad()
+    def __call__(self, batched_inputs: List[dict]):
+        return self.inference(batched_inputs)
+
+    @torch.no_grad()
+    def inference(self, batched_inputs: List[dict], do_postprocess=True):
+        images = self.to_device(batched_inputs)
+        sizes = [tuple(im.shape[-2:]) for im in images]
+        outs = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)] if do_postprocess else sizes
+        boxes, scores, classes, rows, counts = self.engine.run(images, outs)
+        # one packed D2H per batch
+        host = torch.cat([boxes.view(len(images), -1), scores, classes.float(), counts.float()[:, None]], dim=1).cpu()
+        k = scores.shape[1]
+        res = []
+        for i, o in enumerate(outs):
+            c = int(host[i, -1])
+            inst = Instances(o)
+            inst.pred_boxes = Boxes(host[i, : 4 * k].view(k, 4)[:c].clone())
+            inst.scores = host[i, 4 * k: 5 * k][:c].clone()
+            inst.pred_classes = host[i, 5 * k: 6 * k][:c].to(torch.int64)
+            res.append({"instances": inst})
+        return res

@@ -9,6 +9,7 @@ from . import _lib
 from ._lib import BF16, F32, OUT_NCHW, OUT_NHWC, DetParams, FMap, GemmDesc, RpnLevel, RpnParams
 
 _ws = {}
+GEMM_EVENTS = None   # bench.py sets this to a list to time every GEMM launch with CUDA events on the launch stream
 
 
 def _workspace(tag, nbytes, device):
@@ -237,6 +238,12 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
         d.shift[i] = int(s)
     d.relu = int(relu)
     d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
+    if GEMM_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.load().lvcb200_gemm_bf16(ctypes.byref(d), _lib.stream_ptr())
     _lib.check(rc, "lvcb200_gemm_bf16")
+    if GEMM_EVENTS is not None:
+        e1.record()
+        GEMM_EVENTS.append((e0, e1, (M, N, K * taps)))
     return out

@@ -18,11 +18,37 @@ import torch.nn.functional as F
 from . import oracle as O
 
 
-def _conv_bn(sd, prefix, x, stride=1, padding=0, relu=False, eps=1e-5):
+_EMULATE_BF16 = False   # set by detector_forward(emulate_bf16=True): restate the engine's precision policy
+
+
+def _q(x):
+    """Round to bf16 and back (what an activation stored in a bf16 plane goes through)."""
+    return x.bfloat16().float() if _EMULATE_BF16 else x
+
+
+def _conv_bn(sd, prefix, x, stride=1, padding=0, relu=False, eps=1e-5, residual=None, quant_out=True):
+    if _EMULATE_BF16:
+        # engine policy: FrozenBN folded into the weights in fp32, weights cast to bf16, fp32 accumulate,
+        # bias / residual / ReLU in fp32, one rounding to bf16 on store
+        w = sd[prefix + ".weight"].float()
+        if prefix + ".norm.weight" in sd:
+            scale = sd[prefix + ".norm.weight"] * (sd[prefix + ".norm.running_var"] + eps).rsqrt()
+            bias = sd[prefix + ".norm.bias"] - sd[prefix + ".norm.running_mean"] * scale
+            w = w * scale.view(-1, 1, 1, 1)
+        else:
+            bias = sd.get(prefix + ".bias")
+        y = F.conv2d(x, w.bfloat16().float(), bias, stride=stride, padding=padding)
+        if residual is not None:
+            y = y + residual
+        if relu:
+            y = F.relu_(y)
+        return _q(y) if quant_out else y
     x = F.conv2d(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"), stride=stride, padding=padding)
     if prefix + ".norm.weight" in sd:
         x = F.batch_norm(x, sd[prefix + ".norm.running_mean"], sd[prefix + ".norm.running_var"],
                          sd[prefix + ".norm.weight"], sd[prefix + ".norm.bias"], training=False, eps=eps)
+    if residual is not None:
+        x = x + residual
     return F.relu_(x) if relu else x
 
 
@@ -43,7 +69,7 @@ def preprocess(cfg, images):
 
 def resnet(cfg, sd, x, collect=None):
     bu = "backbone.bottom_up."
-    x = _conv_bn(sd, bu + "stem.conv1", x, stride=2, padding=3, relu=True)
+    x = _conv_bn(sd, bu + "stem.conv1", _q(x), stride=2, padding=3, relu=True)
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     if collect is not None:
         collect["stem"] = x
@@ -56,8 +82,7 @@ def resnet(cfg, sd, x, collect=None):
             sc = _conv_bn(sd, p + "shortcut", x, stride=stride) if (p + "shortcut.weight") in sd else x
             out = _conv_bn(sd, p + "conv1", x, stride=stride, relu=True)  # STRIDE_IN_1X1
             out = _conv_bn(sd, p + "conv2", out, padding=1, relu=True)
-            out = _conv_bn(sd, p + "conv3", out)
-            x = F.relu_(out + sc)
+            x = _conv_bn(sd, p + "conv3", out, residual=sc, relu=True)
         feats[f"res{stage}"] = x
     return feats
 
@@ -68,7 +93,7 @@ def fpn(cfg, sd, feats):
     for lvl in (5, 4, 3, 2):
         lat = _conv_bn(sd, f"backbone.fpn_lateral{lvl}", feats[f"res{lvl}"])
         if prev is not None:
-            lat = lat + F.interpolate(prev, scale_factor=2, mode="nearest")
+            lat = _q(lat + F.interpolate(prev, scale_factor=2, mode="nearest"))
         prev = lat
         res[f"p{lvl}"] = _conv_bn(sd, f"backbone.fpn_output{lvl}", prev, padding=1)
     res["p6"] = F.max_pool2d(res["p5"], kernel_size=1, stride=2, padding=0)
@@ -79,9 +104,9 @@ def rpn_head(sd, feats):
     rp = "proposal_generator.rpn_head."
     logits, deltas = [], []
     for name in ("p2", "p3", "p4", "p5", "p6"):
-        t = F.relu(_conv_bn(sd, rp + "conv", feats[name], padding=1))
-        lg = _conv_bn(sd, rp + "objectness_logits", t)
-        dl = _conv_bn(sd, rp + "anchor_deltas", t)
+        t = _conv_bn(sd, rp + "conv", feats[name], padding=1, relu=True)
+        lg = _conv_bn(sd, rp + "objectness_logits", t, quant_out=False)
+        dl = _conv_bn(sd, rp + "anchor_deltas", t, quant_out=False)
         N, A, H, W = lg.shape
         logits.append(lg.permute(0, 2, 3, 1).flatten(1))
         deltas.append(dl.view(N, A, 4, H, W).permute(0, 3, 4, 1, 2).flatten(1, -2))
@@ -105,9 +130,10 @@ def rpn_proposals(cfg, logits, deltas, feat_shapes, image_sizes, nms_mode=None, 
 
 
 def box_head(cfg, sd, pooled, prefix="roi_heads.box_head.", num_fc=None):
-    x = torch.as_tensor(pooled).flatten(1)
+    x = _q(torch.as_tensor(pooled).flatten(1))
     for i in range(num_fc or cfg.num_fc):
-        x = F.relu(F.linear(x, sd[f"{prefix}fc{i + 1}.weight"], sd[f"{prefix}fc{i + 1}.bias"]))
+        w = sd[f"{prefix}fc{i + 1}.weight"]
+        x = _q(F.relu(F.linear(x, _q(w), sd[f"{prefix}fc{i + 1}.bias"])))
     return x
 
 
@@ -117,21 +143,38 @@ def box_predictor(cfg, sd, x):
         xn = x / (torch.norm(x, p=2, dim=1, keepdim=True) + 1e-5)
         w = sd[wp + "cls_score.weight"]
         w = w / (torch.norm(w, p=2, dim=1, keepdim=True) + 1e-5)
-        scores = cfg.cosine_scale * F.linear(xn, w)
+        if _EMULATE_BF16:   # engine: GEMM on the bf16 x and w_hat, then the per-row scale
+            scores = F.linear(x, _q(w)) * (cfg.cosine_scale / (torch.norm(x, p=2, dim=1, keepdim=True) + 1e-5))
+        else:
+            scores = cfg.cosine_scale * F.linear(xn, w)
     else:
-        scores = F.linear(x, sd[wp + "cls_score.weight"], sd[wp + "cls_score.bias"])
-    deltas = F.linear(x, sd[wp + "bbox_pred.weight"], sd[wp + "bbox_pred.bias"])
+        scores = F.linear(x, _q(sd[wp + "cls_score.weight"]), sd[wp + "cls_score.bias"])
+    deltas = F.linear(x, _q(sd[wp + "bbox_pred.weight"]), sd[wp + "bbox_pred.bias"])
     return scores, deltas
 
 
-def detector_forward(cfg, sd, images, out_sizes=None, nms_mode=None, device="cuda", collect=None):
+def detector_forward(cfg, sd, images, out_sizes=None, nms_mode=None, device="cuda", collect=None, emulate_bf16=False):
     """Full candidate-sourcing forward.  images: list of [3,H,W] tensors (BGR, 0..255).
 
     Returns per image dict(pred_boxes, scores, pred_classes).  ``collect`` (dict) receives intermediates.
+    emulate_bf16=True restates the engine's precision policy (bf16 weights with folded FrozenBN, bf16 activation
+    storage, fp32 accumulation) so that the engine can be checked layer by layer at bf16-rounding tolerance.
     """
+    global _EMULATE_BF16
+    _EMULATE_BF16 = bool(emulate_bf16)
+    try:
+        return _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect)
+    finally:
+        _EMULATE_BF16 = False
+
+
+def _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect):
     with torch.no_grad():
         x, sizes = preprocess(cfg, images)
-        feats = fpn(cfg, sd, resnet(cfg, sd, x, collect))
+        res_feats = resnet(cfg, sd, x, collect)
+        if collect is not None:
+            collect["features_res"] = res_feats
+        feats = fpn(cfg, sd, res_feats)
         logits, deltas = rpn_head(sd, feats)
         names = ("p2", "p3", "p4", "p5", "p6")
         shapes = [tuple(feats[n].shape[-2:]) for n in names]
