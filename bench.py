@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gemm-table", default=None, help="write per-GEMM-launch timings of the roofline pass to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -251,6 +252,11 @@ def main():
         torch.cuda.synchronize()
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.GEMM_EVENTS)
         n_gemm = len(ops.GEMM_EVENTS)
+        if args.gemm_table:
+            with open(args.gemm_table, "w") as f:
+                for a, b, (M_, N_, K_) in ops.GEMM_EVENTS:
+                    t_ = a.elapsed_time(b)
+                    f.write(f"M={M_} N={N_} K={K_} ms={t_:.4f} TFLOPs(padded)={2 * M_ * N_ * K_ / t_ / 1e9:.1f}\n")
         ops.GEMM_EVENTS = None
         eng.use_cuda_graph = use_graph
         alg_tflop = algorithmic_gflop_per_image(cfg) * BATCH / 1e3

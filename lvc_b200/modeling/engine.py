@@ -195,6 +195,8 @@ class DetectorEngine:
             off = (p.PW + 1) * 16
             levels.append(dict(logits=head, deltas=head, H=p.H, W=p.W, A=self.A, offset_l=off, offset_d=off + self.A,
                                strides_l=(p.PH * p.PW * 16, p.PW * 16, 16), strides_d=(p.PH * p.PW * 16, p.PW * 16, 16)))
+        if self.debug is not None:
+            self.debug["rpn_levels"] = levels
         return ops.rpn_proposals(levels, sizes_dev, cfg.anchor_sizes, cfg.anchor_ratios, STRIDES, cfg.rpn_pre_nms_topk,
                                  cfg.rpn_post_nms_topk, cfg.rpn_nms_thresh, cfg.rpn_min_box_size, cfg.rpn_bbox_weights)
 

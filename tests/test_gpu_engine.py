@@ -30,36 +30,94 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def _rpn_head_arrays(eng, n):
+    """Engine's fused fp32 [rows,16] RPN head buffers -> reference layout logits [N,HWA], deltas [N,HWA,4]."""
+    logits, deltas = [], []
+    for lv in eng.debug["rpn_levels"]:
+        H, W, A = lv["H"], lv["W"], lv["A"]
+        h = lv["logits"].view(n, H + 2, W + 2, 16)[:, 1:H + 1, 1:W + 1]
+        logits.append(h[..., :A].reshape(n, -1).cpu().numpy())
+        deltas.append(h[..., A:5 * A].reshape(n, -1, 4).cpu().numpy())
+    return logits, deltas
+
+
 @pytest.mark.parametrize("depth,layer,sizes", [(50, "FastRCNNOutputLayers", [(320, 416), (300, 400)]),
                                                (101, "CosineSimOutputLayers", [(256, 320)])])
-def test_engine_vs_bf16_oracle(depth, layer, sizes):
+def test_engine_stagewise_vs_oracle(depth, layer, sizes):
+    """Stage-wise parity: every stage of the engine is checked against the oracle evaluated ON THE ENGINE'S OWN INPUTS to
+    that stage, so that selection steps (top-k, NMS) are compared bit-exactly instead of through accumulated bf16 noise."""
+    from oracle import oracle as O
     cfg = DetectorConfig(depth=depth, output_layer=layer)
     sd = synthetic_state_dict(cfg, 0)
     ims = _images(100, sizes)
+    n = len(ims)
     eng = DetectorEngine(cfg, sd)
     eng.debug = {}
     boxes, scores, classes, rows, counts = eng.run([im.cuda() for im in ims])
     torch.cuda.synchronize()
+    dbg = eng.debug
+    # (1) dense backbone + FPN vs the bf16-emulating oracle (same precision policy): bf16-rounding-level agreement
     col = {}
-    ref = OM.detector_forward(cfg, sd, ims, device="cuda", collect=col, emulate_bf16=True)
+    OM.detector_forward(cfg, sd, ims, device="cuda", collect=col, emulate_bf16=True)
     for l in (2, 3, 4, 5):
-        assert _rel(eng.debug["feats"][l].to_nchw().cpu(), col["features_res"][f"res{l}"]) < 3e-2, f"res{l}"
+        assert _rel(dbg["feats"][l].to_nchw().cpu(), col["features_res"][f"res{l}"]) < 3e-2, f"res{l}"
     for l in (2, 3, 4, 5, 6):
-        assert _rel(eng.debug["pyramid"][l].to_nchw().cpu(), col["features"][f"p{l}"]) < 3e-2, f"p{l}"
-    for n in range(len(ims)):
-        c = int(eng.debug["prop_counts"][n])
-        rb = col["proposals"][n][0]
-        assert abs(c - len(rb)) <= 0.05 * len(rb) + 5
-        m = _iou(rb, eng.debug["props"][n, :c].cpu().numpy()).max(1)
-        assert (m > 0.9).mean() > 0.9                        # >= 90 % of the oracle's proposals reproduced (IoU > 0.9)
-        k = int(counts[n])
-        r = ref[n]
-        assert abs(k - len(r["scores"])) <= 0.2 * len(r["scores"]) + 3
-        if len(r["scores"]):
-            mm = _iou(r["pred_boxes"], boxes[n, :k].cpu().numpy())
-            j = mm.argmax(1)
-            ok = (mm.max(1) > 0.9) & (classes[n, :k].cpu().numpy()[j] == r["pred_classes"])
-            assert ok.mean() > 0.8
+        assert _rel(dbg["pyramid"][l].to_nchw().cpu(), col["features"][f"p{l}"]) < 3e-2, f"p{l}"
+    # (2) RPN head on the engine's pyramid
+    pyr = {f"p{l}": dbg["pyramid"][l].to_nchw().cpu() for l in (2, 3, 4, 5, 6)}
+    OM._EMULATE_BF16 = True
+    try:
+        ref_logits, ref_deltas = OM.rpn_head(sd, pyr)
+    finally:
+        OM._EMULATE_BF16 = False
+    e_logits, e_deltas = _rpn_head_arrays(eng, n)
+    for i in range(5):
+        assert _rel(torch.from_numpy(e_logits[i]), ref_logits[i]) < 1e-2, f"rpn logits level {i}"
+        assert _rel(torch.from_numpy(e_deltas[i]), ref_deltas[i]) < 1e-2, f"rpn deltas level {i}"
+    # (3) proposals from the engine's own logits / deltas: selection and order bit-exact, boxes 1e-3
+    shapes = [(lv["H"], lv["W"]) for lv in dbg["rpn_levels"]]
+    want = OM.rpn_proposals(cfg, [torch.from_numpy(a) for a in e_logits], [torch.from_numpy(a) for a in e_deltas], shapes, sizes, device="cuda")
+    for i in range(n):
+        c = int(dbg["prop_counts"][i])
+        assert c == len(want[i][1])
+        assert np.array_equal(dbg["prop_logits"][i, :c].cpu().numpy(), want[i][1])
+        np.testing.assert_allclose(dbg["props"][i, :c].cpu().numpy(), want[i][0], rtol=1e-3, atol=1e-3)
+    # (4) pooler on the engine's pyramid + proposals (bf16 output: one rounding step)
+    P = dbg["props"].shape[1]
+    props = [dbg["props"][i].cpu().numpy() for i in range(n)]           # all P slots, padded rows are zero boxes
+    ref_pooled, _ = O.roi_pooler([pyr[f"p{l}"].numpy() for l in (2, 3, 4, 5)], props, cfg.pooler_resolution)
+    got = dbg["pooled"].float().permute(0, 3, 1, 2).cpu().numpy()
+    np.testing.assert_allclose(got, ref_pooled, rtol=2 ** -7, atol=1e-3 * np.abs(ref_pooled).max())
+    # (5) box head + predictor on the engine's pooled features
+    OM._EMULATE_BF16 = True
+    try:
+        xh = OM.box_head(cfg, sd, torch.from_numpy(got))
+        ref_scores, ref_deltas2 = OM.box_predictor(cfg, sd, dbg["head"].float().cpu())
+    finally:
+        OM._EMULATE_BF16 = False
+    assert _rel(dbg["head"].float().cpu(), xh) < 1e-2
+    K = cfg.num_classes
+    pred = dbg["pred"].cpu()
+    e_scores = pred[:, :K + 1]
+    if layer == "CosineSimOutputLayers":
+        e_scores = e_scores * (cfg.cosine_scale / (dbg["head"].float().cpu().norm(dim=1, keepdim=True) + 1e-5))
+    assert _rel(e_scores, ref_scores) < 1e-2 and _rel(pred[:, eng.cls_cols:], ref_deltas2) < 1e-2
+    # (6) detections from the engine's own logits / deltas / proposals: classes, rows, order bit-exact
+    probs = O.softmax_rows(e_scores.numpy())
+    dec = O.apply_deltas(pred[:, eng.cls_cols:].numpy(), np.concatenate(props), cfg.roi_bbox_weights)
+    for i in range(n):
+        c = int(dbg["prop_counts"][i])
+        sl = slice(i * P, i * P + c)
+        wb, ws, wc, wr = O.fast_rcnn_inference_single_image(dec[sl], probs[sl], sizes[i], cfg.score_thresh_test, cfg.nms_thresh_test,
+                                                            cfg.detections_per_image, device="cuda")
+        wb, keep = O.detector_postprocess(wb, sizes[i], *sizes[i])
+        k = int(counts[i])
+        assert k == int(keep.sum())
+        # scores within 1e-6 of each other may swap (GPU expf vs libm differ in the last ulp): compare as sets there
+        if not np.array_equal(classes[i, :k].cpu().numpy(), wc[keep]):
+            assert sorted(zip(classes[i, :k].tolist(), rows[i, :k].tolist())) == sorted(zip(wc[keep].tolist(), wr[keep].tolist()))
+        np.testing.assert_allclose(scores[i, :k].cpu().numpy(), ws[keep], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(np.sort(boxes[i, :k].cpu().numpy(), 0), np.sort(wb[keep], 0), rtol=1e-3, atol=1e-2)
 
 
 def test_model_api_vs_golden_fp32(golden):
