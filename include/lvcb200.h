@@ -197,14 +197,16 @@ typedef struct {
 int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d /*host*/, void* stream);
 
 /* Small memory-bound helpers of the conv engine. */
-/* (x - mean) / std, BGR planar fp32 [3,H,W] per image -> stem im2col matrix (7x7/2 pad 3) bf16
- * [n*Hp*Wp (zero-bordered plane of the 1/2-resolution grid), Kpad] ; replaces GeneralizedRCNN.preprocess_image
- * (lvc/modeling/meta_arch/rcnn.py:324-333) + the gather half of BasicStem.conv1 (resnet.py:588-590). */
-int lvcb200_stem_im2col(const float* const* images /*device array of n pointers*/, const int32_t* image_sizes,
-                        int n, int Hpad, int Wpad, const float* mean, const float* inv_std, void* out, int Kpad,
-                        void* stream);
-/* 3x3/2 max-pool (pad 1) between zero-bordered bf16 planes (resnet.py:591). */
-int lvcb200_maxpool3x3s2(const void* in, int n, int H, int W, int C, void* out, void* stream);
+/* Preprocess + 4x4 space-to-depth.  Replaces GeneralizedRCNN.preprocess_image (lvc/modeling/meta_arch/rcnn.py:324-333:
+ * (x - mean) / std, zero pad to /32) and prepares the 7x7/2 stem conv (resnet.py:588-590) as a 3x3 shift-GEMM:
+ * images = device array of n pointers to planar [3,H_i,W_i] images (fp32 or uint8, BGR), image_sizes [n,2] int32 (h,w);
+ * out = zero-bordered bf16 plane [n, Hpad/4 + 2, Wpad/4 + 2, 64] with channel (iy*4+ix)*3 + c (48 used). */
+#define LVCB200_U8 2
+int lvcb200_stem_s2d4(const void* const* images, int image_dtype, const int32_t* image_sizes, int n, int Hpad, int Wpad,
+                      const float* mean, const float* inv_std, void* out, void* stream);
+/* 3x3/2 max-pool (pad 1) (resnet.py:591) over the stem output stored space-to-depth:
+ * in = plane [n, Ho+2, Wo+2, 4*C] with channel ((Y&1)*2 + (X&1))*C + c of stem pixel (Y,X); out = plane [n, Ho+2, Wo+2, C]. */
+int lvcb200_maxpool_s2d(const void* in, int n, int Ho, int Wo, int C, void* out, void* stream);
 /* stride-2 subsample of a zero-bordered plane (input side of the stride-2 1x1 convs, resnet.py:163-171, and
  * LastLevelMaxPool p6, fpn.py:165-177). */
 int lvcb200_subsample2(const void* in, int n, int H, int W, int C, void* out, void* stream);

@@ -67,6 +67,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -134,37 +142,58 @@ struct GemmParams {
   int m_tiles, n_tiles, k_blocks;  // k_blocks per tap
 };
 
-template <int BLOCK_N> struct GemmCfg {
+// MODE 0: direct fp32 stores from registers (tiny heads).  MODE 1: bf16 output staged through a ring of 128x32 smem slots
+// and written with TMA stores.  MODE 2: as 1, and the residual tile is TMA-loaded into the same slot first (the epilogue
+// adds in place), so neither the residual read nor the output write ever stalls a warp on global-memory latency.
+constexpr int kSlotCols = 32;
+constexpr int kSlotBytes = BLOCK_M * kSlotCols * 2;   // 8 KB, 64-byte rows, SWIZZLE_64B
+
+template <int BLOCK_N, int MODE> struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
+  static constexpr int kStages = (MODE == 2) ? ((BLOCK_N >= 256) ? 3 : ((BLOCK_N >= 128) ? 4 : 6))
+                                             : ((BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8));
+  static constexpr int kSlots = (MODE == 0) ? 0 : ((MODE == 2) ? 8 : ((BLOCK_N >= 256) ? 3 : 4));
+  static constexpr int kStoreLag = (MODE == 2) ? 4 : (kSlots - 1);   // TMA stores allowed in flight before a slot is recycled
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 1024 /*barriers + bias*/ + BLOCK_N * 4;
+  static constexpr int kCtrlBytes = 2048;             // barriers, tmem slot, bias tile
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlots * kSlotBytes + kCtrlBytes + 1024 /*align slack*/;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kSlots = Cfg::kSlots;
+  constexpr int kChunksPerTile = BLOCK_N / kSlotCols;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_b0 = smem_base + kStages * Cfg::kStageBytesA;
-  uint8_t* ctrl = smem_al + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);                 // full[kStages], empty[kStages], tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * kStages + 4));
+  const uint32_t smem_slot0 = smem_base + kStages * Cfg::kStageBytes;  // kSlots x 8 KB (1024-aligned)
+  uint8_t* slot_ptr0 = smem_al + kStages * Cfg::kStageBytes;
+  uint8_t* ctrl = slot_ptr0 + kSlots * kSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);   // full[kStages], empty[kStages], tfull[2], tempty[2], sfull[8], sfree[8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * kStages + 4 + 16));
   float* s_bias = reinterpret_cast<float*>(ctrl + 1024);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
   const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_sfull = bar_tempty + 16, bar_sfree = bar_sfull + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_w); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_w);
+    if constexpr (MODE >= 1) tma_prefetch_desc(&tmap_d);
+    if constexpr (MODE == 2) tma_prefetch_desc(&tmap_r);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    for (int s = 0; s < 8; s++) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sfree + 8 * s, 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
@@ -179,6 +208,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) {
     if (lane == 0) {  // ===================================== TMA producer
       uint32_t it = 0;
+      [[maybe_unused]] uint32_t gchunk = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
         for (int t = 0; t < p.taps; t++) {
@@ -188,6 +218,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
             tma_load_2d(smem_a0 + s * Cfg::kStageBytesA, &tmap_a, bar_full + 8 * s, kb * BLOCK_K, m0 + p.shift[t]);
             tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * BLOCK_K, n0);
+          }
+        }
+        if constexpr (MODE == 2) {   // residual chunks of this tile -> slot ring (consumed and overwritten by the epilogue)
+          for (int c = 0; c < kChunksPerTile; c++) {
+            if (n0 + c * kSlotCols >= p.N) break;
+            const uint32_t s = gchunk % kSlots, ph = (gchunk / kSlots) & 1u;
+            mbar_wait(bar_sfree + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_sfull + 8 * s, kSlotBytes);
+            tma_load_2d(smem_slot0 + s * kSlotBytes, &tmap_r, bar_sfull + 8 * s, n0 + c * kSlotCols, m0);
+            gchunk++;
           }
         }
       }
@@ -217,9 +257,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= kEpiWarp0) {  // ========================= epilogue warps
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
-    const int et = threadIdx.x - kEpiWarp0 * 32;      // 0..127
+    const int et = threadIdx.x - kEpiWarp0 * 32;      // 0..127 == row of the tile this thread owns
     constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;
     uint32_t tc = 0;
+    [[maybe_unused]] uint32_t gchunk = 0;             // running slot-ring position (MODE >= 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
       const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
       const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
@@ -228,7 +269,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const long long m = (long long)m0 + q * 32 + lane;
-      bool row_ok = m < p.M;
       bool zero_row = false;
       if (p.plane_h > 0) {
         unsigned int plane = (unsigned)(p.plane_h * p.plane_w);
@@ -241,54 +281,86 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BLOCK_N;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += CH) {
+        if (n0 + c >= p.N) break;                      // uniform: the rest of the tile lies beyond N
         uint32_t v[32];
         if constexpr (CH == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
         tmem_ld_wait();
-        if (n0 + c >= p.N) continue;                   // uniform: whole chunk beyond N
         float f[CH];
 #pragma unroll
         for (int j = 0; j < CH; j++) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
-        if (row_ok) {
-          const int ncols = (p.N - (n0 + c)) < CH ? (p.N - (n0 + c)) : CH;   // multiple of 8
-          if (p.residual != nullptr) {
-            const __nv_bfloat16* rp = p.residual + m * p.ldr + n0 + c;
+        if constexpr (MODE == 0) {
+          if (m < p.M) {
+            const int ncols = (p.N - (n0 + c)) < CH ? (p.N - (n0 + c)) : CH;   // multiple of 8
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              if (j < ncols) {
-                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            for (int j = 0; j < CH; j++) {
+              if (p.relu) f[j] = fmaxf(f[j], 0.f);
+              if (zero_row) f[j] = 0.f;
+            }
+            if (p.d_f32) {
+              float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n0 + c;
 #pragma unroll
-                for (int e = 0; e < 4; e++) { float2 r2 = __bfloat1622float2(h[e]); f[j + 2 * e] += r2.x; f[j + 2 * e + 1] += r2.y; }
+              for (int j = 0; j < CH; j += 4)
+                if (j < ncols) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + m * p.ldd + n0 + c;
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                if (j < ncols) {
+                  uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(f[j + 2 * e], f[j + 2 * e + 1]);
+                  *reinterpret_cast<uint4*>(dp + j) = u;
+                }
               }
             }
           }
+        } else {
+          // ---- slot ring: (residual arrives by TMA) -> add in place -> TMA store
+          const uint32_t s = gchunk % kSlots, ph = (gchunk / kSlots) & 1u;
+          uint8_t* slot = slot_ptr0 + s * kSlotBytes;
+          if constexpr (MODE == 2) mbar_wait(bar_sfull + 8 * s, ph);         // residual chunk has landed
+          else mbar_wait(bar_sfree + 8 * s, ph ^ 1u);                       // previous TMA store from this slot has drained
+          const int r = q * 32 + lane;
+          uint8_t* rowp = slot + r * 64;
+          const int sw = (r >> 1) & 3;                                       // SWIZZLE_64B: 16-byte chunk index ^= addr bits [7,9)
 #pragma unroll
-          for (int j = 0; j < CH; j++) {
-            if (p.relu) f[j] = fmaxf(f[j], 0.f);
-            if (zero_row) f[j] = 0.f;
+          for (int j = 0; j < 4; j++) {
+            uint4* cp = reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4));
+            if constexpr (MODE == 2) {
+              uint4 u = *cp;
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; e++) { float2 r2 = __bfloat1622float2(h[e]); f[8 * j + 2 * e] += r2.x; f[8 * j + 2 * e + 1] += r2.y; }
+            }
+            uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              float a0 = f[8 * j + 2 * e], a1 = f[8 * j + 2 * e + 1];
+              if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+              if (zero_row) { a0 = 0.f; a1 = 0.f; }
+              ho[e] = __floats2bfloat162_rn(a0, a1);
+            }
+            *cp = o;
           }
-          if (p.d_f32) {
-            float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n0 + c;
-#pragma unroll
-            for (int j = 0; j < CH; j += 4)
-              if (j < ncols) *reinterpret_cast<float4*>(dp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + m * p.ldd + n0 + c;
-#pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              if (j < ncols) {
-                uint4 u; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; e++) h[e] = __floats2bfloat162_rn(f[j + 2 * e], f[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(dp + j) = u;
-              }
+          fence_proxy_async();                                               // generic-proxy writes -> visible to the TMA store
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_2d(&tmap_d, smem_slot0 + s * kSlotBytes, n0 + c, m0);  // rows >= M / cols >= N are clipped by the TMA unit
+            tma_store_commit();
+            if (gchunk >= (uint32_t)Cfg::kStoreLag) {
+              tma_store_wait_read<Cfg::kStoreLag>();                         // store (gchunk - lag) has finished reading its slot
+              mbar_arrive(bar_sfree + 8 * ((gchunk - Cfg::kStoreLag) % kSlots));
             }
           }
+          gchunk++;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+    }
+    if constexpr (MODE >= 1) {
+      if (et == 0) tma_store_wait_read<0>();          // smem must stay valid until the last stores have read it
     }
   }
   tc_fence_before();
@@ -330,18 +402,48 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, long long rows, long
   return 0;
 }
 
-template <int BLOCK_N>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t s) {
-  using Cfg = GemmCfg<BLOCK_N>;
+// 2-D bf16 [rows, cols] map for the epilogue slot ring: box = [128 rows x 32 cols], 64-byte swizzle
+static int make_tmap_slot(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(LVCB200_EUNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kSlotCols, (cuuint32_t)BLOCK_M};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "gemm: cuTensorMapEncodeTiled (slot) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+    return LVCB200_EINVAL;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, int MODE>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
+                       cudaStream_t s) {
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_bf16_tc_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tw, p);
+  gemm_bf16_tc_kernel<BLOCK_N, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tw, td, tr, p);
   return check_launch("gemm_bf16_tc_kernel");
+}
+
+template <int BLOCK_N>
+static int launch_gemm_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr,
+                            const GemmParams& p, cudaStream_t s) {
+  if constexpr (BLOCK_N >= 32) {
+    if (mode == 2) return launch_gemm<BLOCK_N, 2>(ta, tw, td, tr, p, s);
+    if (mode == 1) return launch_gemm<BLOCK_N, 1>(ta, tw, td, tr, p, s);
+  }
+  return launch_gemm<BLOCK_N, 0>(ta, tw, td, tr, p, s);
 }
 
 }  // namespace lvcb200
@@ -362,6 +464,10 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   LVC_REQUIRE(d->M < (1ll << 31) && d->M_rows < (1ll << 31), "gemm: M too large");
   int bn = d->N >= 256 ? 256 : (d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16)));
   if (d->N > 128 && d->N < 256) bn = 256;
+  // epilogue mode: fp32 output -> direct stores; bf16 output -> TMA-store slot ring (+ TMA-loaded residual)
+  int mode = d->d_dtype == LVCB200_F32 ? 0 : (d->residual ? 2 : 1);
+  if (mode != 0 && bn < 32) bn = 32;
+  LVC_REQUIRE(!(mode == 0 && d->residual), "gemm: residual with fp32 output is not supported");
   GemmParams p;
   p.bias = d->bias; p.residual = (const __nv_bfloat16*)d->residual; p.ldr = d->ldr;
   p.D = d->D; p.ldd = d->ldd; p.d_f32 = d->d_dtype == LVCB200_F32;
@@ -371,17 +477,20 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   p.m_tiles = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
   p.n_tiles = (d->N + bn - 1) / bn;
   p.k_blocks = (d->K + BLOCK_K - 1) / BLOCK_K;
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, td, tr;
   int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M);
   if (rc) return rc;
   rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn);
   if (rc) return rc;
+  td = ta; tr = ta;  // placeholders when unused (a valid map must still be passed by value)
+  if (mode >= 1 && (rc = make_tmap_slot(&td, d->D, d->M, d->N, d->ldd))) return rc;
+  if (mode == 2 && (rc = make_tmap_slot(&tr, d->residual, d->M, d->N, d->ldr))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tw, p, s);
-    case 128: return launch_gemm<128>(ta, tw, p, s);
-    case 64: return launch_gemm<64>(ta, tw, p, s);
-    case 32: return launch_gemm<32>(ta, tw, p, s);
-    default: return launch_gemm<16>(ta, tw, p, s);
+    case 256: return launch_gemm_mode<256>(mode, ta, tw, td, tr, p, s);
+    case 128: return launch_gemm_mode<128>(mode, ta, tw, td, tr, p, s);
+    case 64: return launch_gemm_mode<64>(mode, ta, tw, td, tr, p, s);
+    case 32: return launch_gemm_mode<32>(mode, ta, tw, td, tr, p, s);
+    default: return launch_gemm_mode<16>(mode, ta, tw, td, tr, p, s);
   }
 }

@@ -5,33 +5,50 @@
 
 namespace lvcb200 {
 
-// (x - mean) / std + zero pad (rcnn.py:324-333, image_list.py:57-119) fused with the patch gather of the 7x7/2
-// stem conv (resnet.py:588-590): row = output pixel of the half-resolution plane, k = c*49 + kh*7 + kw.
+// (x - mean) / std + zero pad to /32 (rcnn.py:324-333, image_list.py:57-119) fused with a 4x4 space-to-depth:
+//   X4[n, y4, x4, (iy*4 + ix)*3 + c] = norm(img[c, 4*y4 + iy, 4*x4 + ix]),  48 channels padded to 64, zero-bordered plane.
+// On X4 the 7x7/stride-2/pad-3 stem conv (resnet.py:588-590) is a 3x3 stride-1 conv with 64 input channels per tap and
+// 4 x 64 output channels (the 2x2 output pixels of each X4 cell), i.e. exactly the shift-GEMM the rest of the network
+// uses -- no im2col matrix (the 832 MB / batch the first version wrote) is ever materialised.
+template <typename T>
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float* const* __restrict__ images, const int32_t* __restrict__ image_sizes, int n, int Ho, int Wo,
-                   const float* __restrict__ mean, const float* __restrict__ inv_std, __nv_bfloat16* __restrict__ out, int Kpad) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int PW = Wo + 2, PH = Ho + 2;
-  const long long rows = (long long)n * PH * PW;
-  if (warp >= rows) return;
-  const int img = (int)(warp / (PH * PW));
-  const int rem = (int)(warp - (long long)img * PH * PW);
+stem_s2d4_kernel(const T* const* __restrict__ images, const int32_t* __restrict__ image_sizes, int n, int H4, int W4,
+                 const float* __restrict__ mean, const float* __restrict__ inv_std, uint4* __restrict__ out) {
+  const int PW = W4 + 2, PH = H4 + 2;
+  const long long total = (long long)n * PH * PW;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = (int)(i / (PH * PW));
+  const int rem = (int)(i - (long long)img * PH * PW);
   const int py = rem / PW, px = rem - py * PW;
-  __nv_bfloat16* o = out + warp * Kpad;
-  const bool border = py == 0 || py == PH - 1 || px == 0 || px == PW - 1;
-  const int H = image_sizes[img * 2], W = image_sizes[img * 2 + 1];
-  const float* im = images[img];
-  const int oy = py - 1, ox = px - 1;
-  for (int k = lane; k < Kpad; k += 32) {
-    float v = 0.f;
-    if (!border && k < 147) {
-      int c = k / 49, r = k - c * 49, kh = r / 7, kw = r - kh * 7;
-      int y = 2 * oy - 3 + kh, x = 2 * ox - 3 + kw;
-      if (y >= 0 && y < H && x >= 0 && x < W) v = (__ldg(im + ((long long)c * H + y) * W + x) - mean[c]) * inv_std[c];
+  uint4* o = out + i * 8;   // 64 bf16 = 8 x 16 bytes
+  __nv_bfloat16 v[64];
+#pragma unroll
+  for (int k = 0; k < 64; k++) v[k] = __float2bfloat16_rn(0.f);
+  if (py >= 1 && py <= H4 && px >= 1 && px <= W4) {
+    const int H = image_sizes[img * 2], W = image_sizes[img * 2 + 1];
+    const T* im = images[img];
+    const int y0 = 4 * (py - 1), x0 = 4 * (px - 1);
+    const float m0 = mean[0], m1 = mean[1], m2 = mean[2], s0 = inv_std[0], s1 = inv_std[1], s2 = inv_std[2];
+#pragma unroll
+    for (int iy = 0; iy < 4; iy++) {
+      const int y = y0 + iy;
+      if (y >= H) continue;
+#pragma unroll
+      for (int ix = 0; ix < 4; ix++) {
+        const int x = x0 + ix;
+        if (x >= W) continue;
+        const long long off = (long long)y * W + x;
+        const long long cs = (long long)H * W;
+        v[(iy * 4 + ix) * 3 + 0] = __float2bfloat16_rn(((float)im[off] - m0) * s0);
+        v[(iy * 4 + ix) * 3 + 1] = __float2bfloat16_rn(((float)im[off + cs] - m1) * s1);
+        v[(iy * 4 + ix) * 3 + 2] = __float2bfloat16_rn(((float)im[off + 2 * cs] - m2) * s2);
+      }
     }
-    o[k] = __float2bfloat16_rn(v);
   }
+  const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++) o[k] = src[k];
 }
 
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
@@ -56,9 +73,10 @@ __device__ __forceinline__ uint4 bf16x8_add(uint4 a, uint4 b) {
   return r;
 }
 
-// F.max_pool2d(k=3, s=2, p=1) (resnet.py:591).  Input is post-ReLU (>= 0), so the zero frame is equivalent to the
-// reference's -inf padding.
-__global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int n, int H, int W, int CV, uint4* __restrict__ out, int Ho, int Wo) {
+// F.max_pool2d(k=3, s=2, p=1) (resnet.py:591) reading the stem output in its space-to-depth layout
+//   S2[n, y2, x2, ((Y&1)*2 + (X&1))*C + c] = stem[n, Y, X, c],  y2 = Y>>1, x2 = X>>1  (zero-bordered plane of the pooled grid)
+// out[n, y, x, c] = max_{dy,dx in -1..1} stem[2y+dy, 2x+dx, c].  Input is post-ReLU (>= 0): the zero frame equals -inf padding.
+__global__ void maxpool_s2d_kernel(const uint4* __restrict__ in, int n, int Ho, int Wo, int CV, uint4* __restrict__ out) {
   const long long total = (long long)n * (Ho + 2) * (Wo + 2) * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int cv = (int)(i % CV);
@@ -66,17 +84,17 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int n, int H, 
     int px = (int)(pix % (Wo + 2)), py = (int)((pix / (Wo + 2)) % (Ho + 2)), img = (int)(pix / ((long long)(Wo + 2) * (Ho + 2)));
     uint4 r = make_uint4(0, 0, 0, 0);
     if (py >= 1 && py <= Ho && px >= 1 && px <= Wo) {
-      int oy = py - 1, ox = px - 1;
-      const uint4* base = in + ((long long)img * (H + 2) * (W + 2)) * CV + cv;
-      // window rows 2*oy-1 .. 2*oy+1 in image coords = 2*oy .. 2*oy+2 in plane coords (always inside the plane)
+      const uint4* base = in + ((long long)img * (Ho + 2) * (Wo + 2)) * (4 * CV);
       bool first = true;
 #pragma unroll
-      for (int dy = 0; dy < 3; dy++)
+      for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-        for (int dx = 0; dx < 3; dx++) {
-          int yy = 2 * oy + dy, xx = 2 * ox + dx;
-          if (yy > H + 1 || xx > W + 1) continue;
-          uint4 v = __ldg(base + ((long long)yy * (W + 2) + xx) * CV);
+        for (int dx = -1; dx <= 1; dx++) {
+          // stem pixel (2*(py-1)+dy, 2*(px-1)+dx): cell = floor(/2) (+1 for the frame), sub-position = parity
+          int Y = 2 * (py - 1) + dy, X = 2 * (px - 1) + dx;
+          int cy = (Y + 2) / 2, cx = (X + 2) / 2;      // (Y>>1) + 1 for Y >= -1
+          int sub = ((Y & 1) * 2 + (X & 1));
+          uint4 v = __ldg(base + ((long long)cy * (Wo + 2) + cx) * (4 * CV) + sub * CV + cv);
           r = first ? v : bf16x8_max(r, v);
           first = false;
         }
@@ -124,23 +142,27 @@ static inline unsigned grid_for(long long total, int threads) {
   return (unsigned)(b < cap ? b : cap);
 }
 
-extern "C" int lvcb200_stem_im2col(const float* const* images, const int32_t* image_sizes, int n, int Hpad, int Wpad,
-                                   const float* mean, const float* inv_std, void* out, int Kpad, void* stream) {
-  LVC_REQUIRE(n >= 1 && Hpad % 2 == 0 && Wpad % 2 == 0 && Kpad >= 147 && Kpad % 8 == 0, "stem_im2col: bad shape");
-  LVC_REQUIRE(images && image_sizes && mean && inv_std && out, "stem_im2col: NULL pointer");
-  const int Ho = Hpad / 2, Wo = Wpad / 2;
-  long long rows = (long long)n * (Ho + 2) * (Wo + 2);
-  stem_im2col_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      images, image_sizes, n, Ho, Wo, mean, inv_std, (__nv_bfloat16*)out, Kpad);
-  return check_launch("stem_im2col_kernel");
+extern "C" int lvcb200_stem_s2d4(const void* const* images, int image_dtype, const int32_t* image_sizes, int n, int Hpad, int Wpad,
+                                 const float* mean, const float* inv_std, void* out, void* stream) {
+  LVC_REQUIRE(n >= 1 && Hpad % 4 == 0 && Wpad % 4 == 0, "stem_s2d4: padded size must be a multiple of 4");
+  LVC_REQUIRE(images && image_sizes && mean && inv_std && out, "stem_s2d4: NULL pointer");
+  const int H4 = Hpad / 4, W4 = Wpad / 4;
+  long long total = (long long)n * (H4 + 2) * (W4 + 2);
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (image_dtype == LVCB200_F32)
+    stem_s2d4_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float* const*)images, image_sizes, n, H4, W4, mean, inv_std, (uint4*)out);
+  else if (image_dtype == LVCB200_U8)
+    stem_s2d4_kernel<unsigned char><<<blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char* const*)images, image_sizes, n, H4, W4, mean, inv_std, (uint4*)out);
+  else
+    return set_error(LVCB200_EINVAL, "stem_s2d4: image dtype must be LVCB200_F32 or LVCB200_U8");
+  return check_launch("stem_s2d4_kernel");
 }
 
-extern "C" int lvcb200_maxpool3x3s2(const void* in, int n, int H, int W, int C, void* out, void* stream) {
-  LVC_REQUIRE(n >= 1 && H >= 2 && W >= 2 && C % 8 == 0 && in && out, "maxpool3x3s2: bad argument");
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+extern "C" int lvcb200_maxpool_s2d(const void* in, int n, int Ho, int Wo, int C, void* out, void* stream) {
+  LVC_REQUIRE(n >= 1 && Ho >= 1 && Wo >= 1 && C % 8 == 0 && in && out, "maxpool_s2d: bad argument");
   long long total = (long long)n * (Ho + 2) * (Wo + 2) * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, n, H, W, C / 8, (uint4*)out, Ho, Wo);
-  return check_launch("maxpool3x3s2_kernel");
+  maxpool_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, n, Ho, Wo, C / 8, (uint4*)out);
+  return check_launch("maxpool_s2d_kernel");
 }
 
 extern "C" int lvcb200_subsample2(const void* in, int n, int H, int W, int C, void* out, void* stream) {

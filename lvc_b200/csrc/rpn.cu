@@ -13,18 +13,30 @@ namespace lvcb200 {
 
 constexpr int kMaxTopk = 1024;
 constexpr int kMaxLevels = 8;
+constexpr int kScanChunk = 2048;   // anchors per CTA in the grid-wide scan kernels
+constexpr int kCandCap = 4096;     // candidate list capacity per (image, level)
 
-struct RpnLevels { lvcb200_rpn_level lv[kMaxLevels]; };
+struct RpnLevels {
+  lvcb200_rpn_level lv[kMaxLevels];
+  int chunk_prefix[kMaxLevels + 1];  // CTA decomposition of one image's anchors over levels (scan kernels)
+};
 
 struct RpnWs {  // element offsets inside the workspace (per (image, level) slot of kMaxTopk entries)
-  size_t off_hdr, off_boxes, off_scores, off_valid, off_kboxes, off_kscores, off_kcount, total;
+  size_t off_hdr, off_boxes, off_scores, off_valid, off_kboxes, off_kscores, off_kcount, off_hist1, off_hist2, off_ccount, off_cand,
+      zero_bytes, total;
 };
 
 static RpnWs rpn_layout(int n_images, int n_levels) {
   RpnWs w; size_t o = 0;
   auto take = [&](size_t b) { size_t r = o; o = align_up(o + b, 256); return r; };
   size_t slots = (size_t)n_images * n_levels;
+  // zero-initialised header region (one memset): per-image hdr, histograms, candidate counters
   w.off_hdr = take(sizeof(uint32_t) * 2 * n_images);  // per image: max coordinate (ordered), valid count
+  w.off_hist1 = take(slots * 2048 * 4);
+  w.off_hist2 = take(slots * 2048 * 4);
+  w.off_ccount = take(slots * 4);
+  w.zero_bytes = o;
+  w.off_cand = take(slots * kCandCap * 8);
   w.off_boxes = take(slots * kMaxTopk * 16);
   w.off_scores = take(slots * kMaxTopk * 4);
   w.off_valid = take(slots * kMaxTopk);
@@ -42,12 +54,129 @@ __device__ __forceinline__ int64_t rpn_addr(int i, int A, int W, int64_t row_str
   return (int64_t)y * row_stride + (int64_t)x * pix_stride + a * mult;
 }
 
+
+// ---- grid-wide top-k selection, phase 1-3 (the single-CTA select in rpn_select_decode_kernel is the fallback for
+// degenerate inputs whose 22-bit key prefix does not separate the k-th value, e.g. an all-equal logit map).
+__device__ __forceinline__ bool rpn_scan_range(const RpnLevels& L, int n_levels, int& img, int& lvl, int& beg, int& end) {
+  const int per_img = L.chunk_prefix[n_levels];
+  img = blockIdx.x / per_img;
+  const int c = blockIdx.x - img * per_img;
+  lvl = 0;
+  while (lvl + 1 < n_levels && c >= L.chunk_prefix[lvl + 1]) lvl++;
+  const int n = L.lv[lvl].H * L.lv[lvl].W * L.lv[lvl].A;
+  beg = (c - L.chunk_prefix[lvl]) * kScanChunk;
+  end = min(beg + kScanChunk, n);
+  return beg < n;
+}
+
+// digit (from the top) at which the suffix count of hist reaches `need`; returns digit, writes count strictly above it
+__device__ __forceinline__ int rpn_find_digit(const unsigned int* __restrict__ hist, unsigned int need, unsigned int* above_out,
+                                              unsigned int* s_tmp /* 2 words smem */) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const int per = 64;
+    unsigned int local = 0;
+    for (int b = 0; b < per; b++) local += hist[lane * per + b];
+    unsigned int suffix = local;
+    for (int o = 1; o < 32; o <<= 1) { unsigned int v = __shfl_down_sync(0xffffffffu, suffix, o); if (lane + o < 32) suffix += v; }
+    unsigned int above = suffix - local;
+    if (above < need && suffix >= need) {
+      unsigned int acc = above; int d = 0;
+      for (int b = per - 1; b >= 0; b--) {
+        unsigned int h = hist[lane * per + b];
+        if (acc + h >= need) { d = lane * per + b; break; }
+        acc += h;
+      }
+      s_tmp[0] = (unsigned)d; s_tmp[1] = acc;
+    }
+  }
+  __syncthreads();
+  *above_out = s_tmp[1];
+  return (int)s_tmp[0];
+}
+
+__global__ void __launch_bounds__(256)
+rpn_hist1_kernel(RpnLevels L, int n_levels, unsigned int* __restrict__ hist1) {
+  __shared__ unsigned int h[2048];
+  int img, lvl, beg, end;
+  if (!rpn_scan_range(L, n_levels, img, lvl, beg, end)) return;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0u;
+  __syncthreads();
+  const lvcb200_rpn_level& lv = L.lv[lvl];
+  const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x)
+    atomicAdd(&h[float_to_ordered(__ldg(logits + rpn_addr(i, lv.A, lv.W, lv.row_stride_l, lv.pix_stride_l, 1))) >> 21], 1u);
+  __syncthreads();
+  unsigned int* g = hist1 + (size_t)(img * n_levels + lvl) * 2048;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) if (h[i]) atomicAdd(&g[i], h[i]);
+}
+
+__global__ void __launch_bounds__(256)
+rpn_hist2_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __restrict__ hist1, unsigned int* __restrict__ hist2) {
+  __shared__ unsigned int h[2048];
+  __shared__ unsigned int tmp[2];
+  int img, lvl, beg, end;
+  if (!rpn_scan_range(L, n_levels, img, lvl, beg, end)) return;
+  const lvcb200_rpn_level& lv = L.lv[lvl];
+  const int n = lv.H * lv.W * lv.A;
+  const unsigned int k = (unsigned)(topk < n ? topk : n);
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0u;
+  unsigned int above;
+  const unsigned int d1 = (unsigned)rpn_find_digit(hist1 + (size_t)(img * n_levels + lvl) * 2048, k, &above, tmp);
+  const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    unsigned int key = float_to_ordered(__ldg(logits + rpn_addr(i, lv.A, lv.W, lv.row_stride_l, lv.pix_stride_l, 1)));
+    if ((key >> 21) == d1) atomicAdd(&h[(key >> 10) & 2047u], 1u);
+  }
+  __syncthreads();
+  unsigned int* g = hist2 + (size_t)(img * n_levels + lvl) * 2048;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) if (h[i]) atomicAdd(&g[i], h[i]);
+}
+
+__global__ void __launch_bounds__(256)
+rpn_collect_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __restrict__ hist1, const unsigned int* __restrict__ hist2,
+                   unsigned int* __restrict__ ccount, unsigned long long* __restrict__ cand) {
+  __shared__ unsigned int tmp[2];
+  int img, lvl, beg, end;
+  if (!rpn_scan_range(L, n_levels, img, lvl, beg, end)) return;
+  const lvcb200_rpn_level& lv = L.lv[lvl];
+  const int n = lv.H * lv.W * lv.A;
+  const unsigned int k = (unsigned)(topk < n ? topk : n);
+  const int slot = img * n_levels + lvl;
+  unsigned int above1, above2;
+  const unsigned int d1 = (unsigned)rpn_find_digit(hist1 + (size_t)slot * 2048, k, &above1, tmp);
+  __syncthreads();
+  const unsigned int d2 = (unsigned)rpn_find_digit(hist2 + (size_t)slot * 2048, k - above1, &above2, tmp);
+  const unsigned int t22 = (d1 << 11) | d2;   // every key with a 22-bit prefix >= t22 is a candidate (>= k of them)
+  const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
+  const int lane = threadIdx.x & 31;
+  for (int i0 = beg; i0 < end; i0 += blockDim.x) {
+    int i = i0 + threadIdx.x;
+    unsigned int key = 0; bool take = false;
+    if (i < end) {
+      key = float_to_ordered(__ldg(logits + rpn_addr(i, lv.A, lv.W, lv.row_stride_l, lv.pix_stride_l, 1)));
+      take = (key >> 10) >= t22;
+    }
+    unsigned int m = __ballot_sync(0xffffffffu, take);
+    if (m) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(&ccount[slot], (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) {
+        unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < (unsigned)kCandCap) cand[(size_t)slot * kCandCap + pos] = ((unsigned long long)key << 32) | (unsigned int)(~(unsigned int)i);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024)
 rpn_select_decode_kernel(RpnLevels L, int n_levels, int topk, float min_box_size, float wx, float wy, float ww, float wh,
                          const int32_t* __restrict__ image_sizes, float4* __restrict__ ws_boxes, float* __restrict__ ws_scores,
-                         unsigned char* __restrict__ ws_valid, uint32_t* __restrict__ hdr) {
+                         unsigned char* __restrict__ ws_valid, uint32_t* __restrict__ hdr, const unsigned int* __restrict__ ccount,
+                         const unsigned long long* __restrict__ cand) {
   __shared__ unsigned int hist[2048];
-  __shared__ unsigned long long sel[kMaxTopk];
+  __shared__ unsigned long long sel[kCandCap];
   __shared__ unsigned int warp_gt[32], warp_eq[32];
   __shared__ unsigned int s_prefix, s_need;
   const int img = blockIdx.x / n_levels, lvl = blockIdx.x % n_levels;
@@ -57,7 +186,16 @@ rpn_select_decode_kernel(RpnLevels L, int n_levels, int topk, float min_box_size
   const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-  // ---- exact radix select of the k-th largest key: 11 + 11 + 10 bits
+  const unsigned int n_cand = ccount ? ccount[blockIdx.x] : 0xffffffffu;
+  if (n_cand <= (unsigned)kCandCap) {
+    // ---- fast path: the grid-wide scan kernels left <= 4096 candidates (all keys >= the 22-bit threshold prefix);
+    //      sort them (key desc, index asc): the first k are the reference's sorted top-k
+    for (int i = tid; i < kCandCap; i += blockDim.x) sel[i] = (i < (int)n_cand) ? cand[(size_t)blockIdx.x * kCandCap + i] : 0ull;
+    __syncthreads();
+    int np2 = 1024; while (np2 < (int)n_cand) np2 <<= 1;
+    bitonic_sort_desc(sel, np2);
+  } else {
+  // ---- fallback: exact radix select of the k-th largest key over all anchors by this CTA alone: 11 + 11 + 10 bits
   unsigned int prefix = 0u, mask = 0u, need = (unsigned)k;
   const int shifts[3] = {21, 10, 0};
   const int bits[3] = {11, 11, 10};
@@ -101,6 +239,7 @@ rpn_select_decode_kernel(RpnLevels L, int n_levels, int topk, float min_box_size
 
   // ---- ordered compaction
   for (int i = tid; i < kMaxTopk; i += blockDim.x) sel[i] = 0ull;
+  __syncthreads();
   unsigned int base_gt = 0, base_eq = 0;
   for (int i0 = 0; i0 < n; i0 += blockDim.x) {
     int i = i0 + tid;
@@ -128,6 +267,7 @@ rpn_select_decode_kernel(RpnLevels L, int n_levels, int topk, float min_box_size
     __syncthreads();
   }
   bitonic_sort_desc(sel, kMaxTopk);
+  }
 
   // ---- decode the selected anchors
   const int slot0 = (img * n_levels + lvl) * kMaxTopk;
@@ -276,8 +416,10 @@ extern "C" int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels, const lvcb
   RpnWs w = rpn_layout(p->n_images, p->n_levels);
   if (workspace_bytes < w.total) return set_error(LVCB200_EWORKSPACE, "rpn_proposals: workspace too small");
   RpnLevels L;
+  L.chunk_prefix[0] = 0;
   for (int i = 0; i < p->n_levels; i++) {
     L.lv[i] = levels[i];
+    L.chunk_prefix[i + 1] = L.chunk_prefix[i] + (levels[i].H * levels[i].W * levels[i].A + kScanChunk - 1) / kScanChunk;
     LVC_REQUIRE(levels[i].A >= 1 && levels[i].A <= 3, "rpn_proposals: A must be 1..3");
     LVC_REQUIRE(levels[i].logits && levels[i].deltas, "rpn_proposals: NULL level pointer");
     LVC_REQUIRE((int64_t)levels[i].H * levels[i].W * levels[i].A < (1ll << 31), "rpn_proposals: level too large");
@@ -285,12 +427,24 @@ extern "C" int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels, const lvcb
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   uint32_t* hdr = (uint32_t*)(ws + w.off_hdr);
-  LVC_CUDA(cudaMemsetAsync(hdr, 0, sizeof(uint32_t) * 2 * p->n_images, s));
+  LVC_CUDA(cudaMemsetAsync(ws, 0, w.zero_bytes, s));
   const int grid = p->n_images * p->n_levels;
+  const int scan_grid = p->n_images * L.chunk_prefix[p->n_levels];
+  unsigned int* hist1 = (unsigned int*)(ws + w.off_hist1);
+  unsigned int* hist2 = (unsigned int*)(ws + w.off_hist2);
+  unsigned int* ccount = (unsigned int*)(ws + w.off_ccount);
+  unsigned long long* cand = (unsigned long long*)(ws + w.off_cand);
+  int rc;
+  rpn_hist1_kernel<<<scan_grid, 256, 0, s>>>(L, p->n_levels, hist1);
+  if ((rc = check_launch("rpn_hist1_kernel"))) return rc;
+  rpn_hist2_kernel<<<scan_grid, 256, 0, s>>>(L, p->n_levels, p->pre_nms_topk, hist1, hist2);
+  if ((rc = check_launch("rpn_hist2_kernel"))) return rc;
+  rpn_collect_kernel<<<scan_grid, 256, 0, s>>>(L, p->n_levels, p->pre_nms_topk, hist1, hist2, ccount, cand);
+  if ((rc = check_launch("rpn_collect_kernel"))) return rc;
   rpn_select_decode_kernel<<<grid, 1024, 0, s>>>(L, p->n_levels, p->pre_nms_topk, p->min_box_size, p->weights[0], p->weights[1],
                                                  p->weights[2], p->weights[3], image_sizes, (float4*)(ws + w.off_boxes),
-                                                 (float*)(ws + w.off_scores), (unsigned char*)(ws + w.off_valid), hdr);
-  int rc = check_launch("rpn_select_decode_kernel");
+                                                 (float*)(ws + w.off_scores), (unsigned char*)(ws + w.off_valid), hdr, ccount, cand);
+  rc = check_launch("rpn_select_decode_kernel");
   if (rc) return rc;
   rpn_nms_kernel<<<grid, 256, 0, s>>>(p->n_levels, p->pre_nms_topk, p->nms_thresh, p->nms_mode, (const float4*)(ws + w.off_boxes),
                                       (const float*)(ws + w.off_scores), (const unsigned char*)(ws + w.off_valid), hdr,

@@ -57,11 +57,25 @@ class DetectorEngine:
         sd = state_dict
         dev = self.device
         bu = "backbone.bottom_up."
-        # stem: K = 147 padded to 192 (3 K-blocks of 64)
+        # stem 7x7/2 conv as a 3x3 shift-GEMM over the 4x4 space-to-depth image (see misc.cu: stem_s2d4_kernel):
+        # W4[(py*2+px)*64 + o, (ty*3+tx)*64 + (iy*4+ix)*3 + c] = w[o, c, kh, kw], kh = 4ty + iy - 2py - 1, kw = 4tx + ix - 2px - 1
         w, b = _fold_bn(sd, bu + "stem.conv1")
-        ws = torch.zeros(64, 192)
-        ws[:, :147] = w.reshape(64, 147)
-        self.stem_w, self.stem_b = ws.to(dev, torch.bfloat16), b.to(dev)
+        w4 = torch.zeros(2, 2, 64, 3, 3, 64)
+        for py in range(2):
+            for px in range(2):
+                for ty in range(3):
+                    for iy in range(4):
+                        kh = 4 * ty + iy - 2 * py - 1
+                        if not 0 <= kh < 7:
+                            continue
+                        for tx in range(3):
+                            for ix in range(4):
+                                kw = 4 * tx + ix - 2 * px - 1
+                                if 0 <= kw < 7:
+                                    ch = (iy * 4 + ix) * 3
+                                    w4[py, px, :, ty, tx, ch:ch + 3] = w[:, :, kh, kw]
+        self.stem_w = w4.reshape(256, 576).to(dev, torch.bfloat16)
+        self.stem_b = b.repeat(4).to(dev)
         self.blocks = []
         for si, nblocks in enumerate(cfg.blocks_per_stage):
             stage = si + 2
@@ -148,16 +162,20 @@ class DetectorEngine:
         return out
 
     # ------------------------------------------------------------------ forward pieces
-    def backbone(self, img_ptrs, sizes_dev, n, Hpad, Wpad):
+    def backbone(self, img_ptrs, img_dtype, sizes_dev, n, Hpad, Wpad):
         lib = _lib.load()
-        Ho, Wo = Hpad // 2, Wpad // 2
-        col = self._buf("stem_col", (n * (Ho + 2) * (Wo + 2), 192))
-        _lib.check(lib.lvcb200_stem_im2col(_lib.ptr(img_ptrs), _lib.ptr(sizes_dev), n, Hpad, Wpad, _lib.ptr(self.mean),
-                                           _lib.ptr(self.inv_std), _lib.ptr(col), 192, _lib.stream_ptr()), "stem_im2col")
-        stem = self._plane("stem", n, Ho, Wo, 64)
-        ops.gemm(col, self.stem_w, bias=self.stem_b, out=stem.t.view(-1, 64), relu=True, K=192, plane_hw=(Ho + 2, Wo + 2))
-        x = self._plane("pool", n, Ho // 2, Wo // 2, 64)
-        _lib.check(lib.lvcb200_maxpool3x3s2(_lib.ptr(stem.t), n, Ho, Wo, 64, _lib.ptr(x.t), _lib.stream_ptr()), "maxpool")
+        H4, W4 = Hpad // 4, Wpad // 4
+        x4 = self._plane("stem_x4", n, H4, W4, 64)
+        _lib.check(lib.lvcb200_stem_s2d4(_lib.ptr(img_ptrs), img_dtype, _lib.ptr(sizes_dev), n, Hpad, Wpad, _lib.ptr(self.mean),
+                                         _lib.ptr(self.inv_std), _lib.ptr(x4.t), _lib.stream_ptr()), "stem_s2d4")
+        s2 = self._plane("stem_s2", n, H4, W4, 256)     # stem output, 2x2 pixels per cell: channel ((Y&1)*2 + (X&1))*64 + o
+        PW = x4.PW
+        ops.gemm(x4.t.view(-1, 64), self.stem_w, bias=self.stem_b, out=s2.t.view(-1, 256), relu=True, taps=9,
+                 shifts=[(ty - 1) * PW + (tx - 1) for ty in range(3) for tx in range(3)], K=64, plane_hw=(x4.PH, x4.PW))
+        x = self._plane("pool", n, H4, W4, 64)
+        _lib.check(lib.lvcb200_maxpool_s2d(_lib.ptr(s2.t), n, H4, W4, 64, _lib.ptr(x.t), _lib.stream_ptr()), "maxpool_s2d")
+        if self.debug is not None:
+            self.debug["stem_pool"] = x
         feats = {}
         for i, blk in enumerate(self.blocks):
             tag = f"b{i}"
@@ -226,8 +244,8 @@ class DetectorEngine:
                               nms_thresh=cfg.nms_thresh_test, topk=cfg.detections_per_image, row_scale=row_scale)
 
     # ------------------------------------------------------------------ whole forward on device-resident inputs
-    def forward_device(self, img_ptrs, sizes_dev, out_sizes_dev, n, Hpad, Wpad):
-        feats = self.backbone(img_ptrs, sizes_dev, n, Hpad, Wpad)
+    def forward_device(self, img_ptrs, img_dtype, sizes_dev, out_sizes_dev, n, Hpad, Wpad):
+        feats = self.backbone(img_ptrs, img_dtype, sizes_dev, n, Hpad, Wpad)
         pyramid = self.fpn(feats)
         props, plogits, counts = self.rpn(pyramid, sizes_dev)
         if self.debug is not None:
@@ -235,17 +253,21 @@ class DetectorEngine:
         return self.roi_heads(pyramid, props, counts, sizes_dev, out_sizes_dev)
 
     def run(self, images: List[torch.Tensor], out_sizes=None):
-        """images: list of fp32 [3,H,W] CUDA tensors (BGR, 0..255).  Returns (boxes [n,100,4], scores, classes, rows, counts)."""
+        """images: list of [3,H,W] CUDA tensors (BGR, 0..255), all fp32 or all uint8 (what the reference's DatasetMapper yields).
+        Returns (boxes [n,100,4], scores, classes, rows, counts)."""
         _lib.require_cuda(*images)
         cfg = self.cfg
         n = len(images)
-        images = [im.contiguous().float() for im in images]
+        if all(im.dtype == torch.uint8 for im in images):
+            images, img_dtype = [im.contiguous() for im in images], _lib.U8
+        else:
+            images, img_dtype = [im.contiguous().float() for im in images], _lib.F32
         sizes = [tuple(im.shape[-2:]) for im in images]
         d = cfg.size_divisibility
         Hpad = (max(s[0] for s in sizes) + d - 1) // d * d
         Wpad = (max(s[1] for s in sizes) + d - 1) // d * d
         out_sizes = out_sizes or sizes
-        key = (n, Hpad, Wpad)
+        key = (n, Hpad, Wpad, img_dtype)
         st = self._graphs.get(key)
         if st is None:
             st = dict(ptrs=torch.zeros(n, dtype=torch.int64, device=self.device),
@@ -257,15 +279,15 @@ class DetectorEngine:
         st["outs"].copy_(torch.tensor(out_sizes, dtype=torch.int32))
         self._keepalive = images
         if not self.use_cuda_graph or self.debug is not None:
-            return self.forward_device(st["ptrs"], st["sizes"], st["outs"], n, Hpad, Wpad)
+            return self.forward_device(st["ptrs"], img_dtype, st["sizes"], st["outs"], n, Hpad, Wpad)
         if st["graph"] is None:
             if st["warm"] < 1:   # first call eager: allocates every buffer, sets kernel attributes
                 st["warm"] += 1
-                return self.forward_device(st["ptrs"], st["sizes"], st["outs"], n, Hpad, Wpad)
+                return self.forward_device(st["ptrs"], img_dtype, st["sizes"], st["outs"], n, Hpad, Wpad)
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
-                st["result"] = self.forward_device(st["ptrs"], st["sizes"], st["outs"], n, Hpad, Wpad)
+                st["result"] = self.forward_device(st["ptrs"], img_dtype, st["sizes"], st["outs"], n, Hpad, Wpad)
             st["graph"] = g
         st["graph"].replay()
         return st["result"]

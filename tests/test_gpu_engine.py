@@ -59,6 +59,7 @@ def test_engine_stagewise_vs_oracle(depth, layer, sizes):
     # (1) dense backbone + FPN vs the bf16-emulating oracle (same precision policy): bf16-rounding-level agreement
     col = {}
     OM.detector_forward(cfg, sd, ims, device="cuda", collect=col, emulate_bf16=True)
+    assert _rel(dbg["stem_pool"].to_nchw().cpu(), col["stem"]) < 1e-2, "stem (7x7/2 conv as s2d shift-GEMM) + maxpool"
     for l in (2, 3, 4, 5):
         assert _rel(dbg["feats"][l].to_nchw().cpu(), col["features_res"][f"res{l}"]) < 3e-2, f"res{l}"
     for l in (2, 3, 4, 5, 6):
@@ -151,3 +152,16 @@ def test_cuda_graph_replay_is_deterministic():
     torch.cuda.synchronize()
     for a, b in zip(eager, out):
         assert torch.equal(a, b)
+
+
+def test_uint8_images_match_float_images():
+    """DatasetMapper yields uint8 BGR images; the stem kernel reads them directly (4x less H2D traffic)."""
+    cfg = DetectorConfig(depth=50)
+    sd = synthetic_state_dict(cfg, 0)
+    u8 = [(torch.rand(3, 200, 264, generator=torch.Generator().manual_seed(3)) * 255).to(torch.uint8).cuda()]
+    eng = DetectorEngine(cfg, sd)
+    a = eng.run(u8)
+    b = eng.run([u8[0].float()])
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

@@ -191,6 +191,36 @@ def test_rpn_topk_ties_and_small_levels():
     np.testing.assert_allclose(p[0, : int(c[0])].cpu().numpy(), anchors[keep], rtol=0, atol=1e-5)
 
 
+def test_rpn_topk_degenerate_fallback_and_big_level():
+    """A large all-equal logit map overflows the candidate list (22-bit prefix cannot separate) -> single-CTA exact select;
+    and a large random level goes through the grid-wide scan path.  Both against the oracle."""
+    H, W, A = 60, 70, 3
+    n = H * W * A
+    rng = np.random.default_rng(5)
+    sizes = [(480, 560)]
+    for kind in ("equal", "random", "few_distinct"):
+        if kind == "equal":
+            lg = np.zeros((1, n), np.float32)
+        elif kind == "random":
+            lg = (rng.permutation(n).astype(np.float32) / n * 10 - 5).reshape(1, n)
+        else:
+            lg = rng.integers(0, 3, (1, n)).astype(np.float32)          # massive ties at the k-th value
+        dl = (rng.standard_normal((1, n, 4)) * 0.3).astype(np.float32)
+        p, l, c = ops.rpn_proposals([ops.rpn_level_dense(cu(lg), cu(dl), H, W, A)], cu(np.array(sizes, np.int32)), (64,), (0.5, 1.0, 2.0),
+                                    strides=(8,), pre_nms_topk=1000, post_nms_topk=1000, nms_thresh=0.7, nms_mode=1)
+        cell = O.cell_anchors([64], (0.5, 1.0, 2.0))
+        anchors = O.grid_anchors(cell, H, W, 8)
+        props = O.apply_deltas(dl.reshape(-1, 4), anchors, (1, 1, 1, 1)).reshape(1, n, 4)
+        want = O.find_top_rpn_proposals([props], [lg], sizes, nms_mode=O.VANILLA)
+        c = int(c[0])
+        assert c == len(want[0][1]), kind
+        if kind == "random":
+            assert np.array_equal(l[0, :c].cpu().numpy(), want[0][1])
+            np.testing.assert_allclose(p[0, :c].cpu().numpy(), want[0][0], rtol=1e-3, atol=1e-3)
+        else:   # tied scores: same selected set (stable index order), NMS order among equal scores follows index order too
+            np.testing.assert_allclose(p[0, :c].cpu().numpy(), want[0][0], rtol=1e-3, atol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------ box-head post-processing
 @pytest.mark.parametrize("thr", [0.05, 0.0])
 @pytest.mark.parametrize("mode", [0, 1])
