@@ -151,6 +151,14 @@ int lvcb200_detections(const float* cls_logits, int64_t logit_pitch, const float
                        float* det_boxes, float* det_scores, int64_t* det_classes, int64_t* det_rows, int32_t* det_counts,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Class-agnostic box update of the box corrector.  Replaces BoxOnlyLayersCascade.predict_boxes
+ * (lvc/modeling/roi_heads/roi_heads_cascade.py:197-211 -> Box2BoxTransform.apply_deltas, box_regression.py:73-110) followed
+ * by Boxes.clip (CascadeROIHeads._create_proposals_from_boxes, cascade_rcnn.py:348-369).  boxes [R,4], deltas [R,>=4] (row pitch
+ * delta_pitch), roi_image [R] int32, image_sizes [n,2] int32 (h,w), weights4 = host float[4]; clip != 0 clips to the image. */
+int lvcb200_apply_deltas_clip(const float* boxes, const float* deltas, int64_t delta_pitch, const int32_t* roi_image,
+                              const int32_t* image_sizes, int64_t R, const float* weights4 /*host*/, int clip, float* out,
+                              void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * kNN label verification.  Replaces run_nearest_neighbours + get_nn_class_confirmatory
  * (tools/run_nearest_neighbours.py:142-162, 214-227): centred cosine similarity against the support bank,

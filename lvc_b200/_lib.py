@@ -63,6 +63,8 @@ _SIGS = {
     "lvcb200_detections": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                                    POINTER(DetParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lvcb200_apply_deltas_clip": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, POINTER(c_float), c_int, c_void_p,
+                                          c_void_p]),
     "lvcb200_knn_prepared_bytes": (c_size_t, [c_int, c_int]),
     "lvcb200_knn_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_knn_verify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,

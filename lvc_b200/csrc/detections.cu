@@ -241,6 +241,34 @@ det_merge_kernel(int K, int topk, const int* __restrict__ kcount, const float* _
   }
 }
 
+// Box2BoxTransform.apply_deltas (box_regression.py:73-110) for class-agnostic deltas + Boxes.clip: the per-stage box update of
+// the box corrector (BoxOnlyLayersCascade.predict_boxes roi_heads_cascade.py:197-211; _create_proposals_from_boxes
+// cascade_rcnn.py:348-369).
+__global__ void apply_deltas_clip_kernel(const float4* __restrict__ boxes, const float* __restrict__ deltas, int64_t delta_pitch,
+                                         const int32_t* __restrict__ roi_image, const int32_t* __restrict__ image_sizes, int64_t R,
+                                         float wx, float wy, float ww, float wh, int clip, float4* __restrict__ out) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float4 p = boxes[r];
+  const float* d = deltas + r * delta_pitch;
+  const float clampv = 4.135166556742356f;
+  const float widths = __fsub_rn(p.z, p.x), heights = __fsub_rn(p.w, p.y);
+  const float cx = __fadd_rn(p.x, __fmul_rn(0.5f, widths)), cy = __fadd_rn(p.y, __fmul_rn(0.5f, heights));
+  float dx = __fdiv_rn(d[0], wx), dy = __fdiv_rn(d[1], wy);
+  float dw = fminf(__fdiv_rn(d[2], ww), clampv), dh = fminf(__fdiv_rn(d[3], wh), clampv);
+  float pcx = __fadd_rn(__fmul_rn(dx, widths), cx), pcy = __fadd_rn(__fmul_rn(dy, heights), cy);
+  float pw = __fmul_rn(expf(dw), widths), ph = __fmul_rn(expf(dh), heights);
+  float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  float x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)), y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+  if (clip) {
+    const int img = roi_image[r];
+    const float ih = (float)image_sizes[img * 2], iw = (float)image_sizes[img * 2 + 1];
+    x1 = fminf(fmaxf(x1, 0.f), iw); y1 = fminf(fmaxf(y1, 0.f), ih);
+    x2 = fminf(fmaxf(x2, 0.f), iw); y2 = fminf(fmaxf(y2, 0.f), ih);
+  }
+  out[r] = make_float4(x1, y1, x2, y2);
+}
+
 __global__ void det_first_row_kernel(const int32_t* __restrict__ roi_image, int64_t R, int32_t* __restrict__ first_row) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
@@ -299,4 +327,17 @@ extern "C" int lvcb200_detections(const float* cls_logits, int64_t logit_pitch, 
       (const float4*)(ws + w.off_cbox), image_sizes, out_sizes, (float4*)(ws + w.off_tmp_boxes), (float*)(ws + w.off_tmp_scores),
       (int*)(ws + w.off_tmp_cls), (int*)(ws + w.off_tmp_rows), (float4*)det_boxes, det_scores, det_classes, det_rows, det_counts);
   return check_launch("det_merge_kernel");
+}
+
+extern "C" int lvcb200_apply_deltas_clip(const float* boxes, const float* deltas, int64_t delta_pitch, const int32_t* roi_image,
+                                         const int32_t* image_sizes, int64_t R, const float* weights4 /*host*/, int clip, float* out,
+                                         void* stream) {
+  if (R == 0) return 0;
+  LVC_REQUIRE(boxes && deltas && out && weights4, "apply_deltas_clip: NULL pointer");
+  LVC_REQUIRE(!clip || (roi_image && image_sizes), "apply_deltas_clip: clip needs roi_image and image_sizes");
+  LVC_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)out % 16) == 0, "apply_deltas_clip: boxes must be 16-byte aligned");
+  apply_deltas_clip_kernel<<<(unsigned)ceil_div64(R, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)boxes, deltas, delta_pitch, roi_image, image_sizes, R, weights4[0], weights4[1], weights4[2], weights4[3], clip,
+      (float4*)out);
+  return check_launch("apply_deltas_clip_kernel");
 }

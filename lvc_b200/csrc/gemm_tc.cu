@@ -133,70 +133,86 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 
 struct GemmParams {
   const float* bias;
-  const __nv_bfloat16* residual; long long ldr;
   void* D; long long ldd; int d_f32;
   long long M; int N; int K;
   int taps; int shift[9];
   int relu;
   int plane_h, plane_w;
   int m_tiles, n_tiles, k_blocks;  // k_blocks per tap
+  int has_res;                     // residual tile added on the tensor core: D += R_tile * I (identity B operand)
+  int num_stages;                  // smem pipeline depth (runtime: deep for big-K layers, shallow + big staging for small-K)
+  int phase_cols;                  // MODE 1: output columns staged per TMA-store phase (64 or 128)
 };
 
-// MODE 0: direct fp32 stores from registers (tiny heads).  MODE 1: bf16 output staged through a ring of 128x32 smem slots
-// and written with TMA stores.  MODE 2: as 1, and the residual tile is TMA-loaded into the same slot first (the epilogue
-// adds in place), so neither the residual read nor the output write ever stalls a warp on global-memory latency.
-constexpr int kSlotCols = 32;
-constexpr int kSlotBytes = BLOCK_M * kSlotCols * 2;   // 8 KB, 64-byte rows, SWIZZLE_64B
+// MODE 0: epilogue stores straight from registers (fp32 heads, tiny N).
+// MODE 1: bf16 output: TMEM -> registers -> (bias, ReLU, border zero) -> 128B-swizzled smem staging (double buffered) -> TMA
+//         store; one fence + two CTA-local barriers per 64/128 output columns, stores complete asynchronously.
+// The residual never touches the epilogue: its [128 x 64] tiles ride the operand pipeline as extra K-steps against an
+// identity matrix (exact: bf16 * 1.0 accumulated in fp32), so D = A*W + R leaves the tensor core already summed.
+constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int kIdentBytes = 64 * 64 * 2;              // 8 KB
+constexpr int kCtrlBytes = 2048;
+constexpr int kMaxStages = 8;
 
-template <int BLOCK_N, int MODE> struct GemmCfg {
-  static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
+template <int BLOCK_N> struct GemmCfg {
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (MODE == 2) ? ((BLOCK_N >= 256) ? 3 : ((BLOCK_N >= 128) ? 4 : 6))
-                                             : ((BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8));
-  static constexpr int kSlots = (MODE == 0) ? 0 : ((MODE == 2) ? 8 : ((BLOCK_N >= 256) ? 3 : 4));
-  static constexpr int kStoreLag = (MODE == 2) ? 4 : (kSlots - 1);   // TMA stores allowed in flight before a slot is recycled
   static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int kCtrlBytes = 2048;             // barriers, tmem slot, bias tile
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSlots * kSlotBytes + kCtrlBytes + 1024 /*align slack*/;
 };
+
+__host__ __device__ inline int gemm_smem_bytes(int block_n, int mode, int num_stages, int phase_cols, int has_res) {
+  int b = num_stages * (kStageBytesA + block_n * BLOCK_K * 2);
+  if (mode == 1) b += 2 * BLOCK_M * phase_cols * 2;
+  if (has_res) b += kIdentBytes;
+  return b + kCtrlBytes + 1024 /*alignment slack*/;
+}
 
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, MODE>;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kSlots = Cfg::kSlots;
-  constexpr int kChunksPerTile = BLOCK_N / kSlotCols;
+  using Cfg = GemmCfg<BLOCK_N>;
+  const int kStages = p.num_stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a0 = smem_base;
-  const uint32_t smem_b0 = smem_base + kStages * Cfg::kStageBytesA;
-  const uint32_t smem_slot0 = smem_base + kStages * Cfg::kStageBytes;  // kSlots x 8 KB (1024-aligned)
-  uint8_t* slot_ptr0 = smem_al + kStages * Cfg::kStageBytes;
-  uint8_t* ctrl = slot_ptr0 + kSlots * kSlotBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);   // full[kStages], empty[kStages], tfull[2], tempty[2], sfull[8], sfree[8]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * kStages + 4 + 16));
+  const uint32_t smem_b0 = smem_base + kStages * kStageBytesA;
+  const uint32_t off_staging = kStages * Cfg::kStageBytes;
+  const uint32_t staging_bytes = (MODE == 1) ? 2u * BLOCK_M * p.phase_cols * 2u : 0u;
+  const uint32_t off_ident = off_staging + staging_bytes;
+  const uint32_t off_ctrl = off_ident + (p.has_res ? kIdentBytes : 0);
+  uint8_t* ctrl = smem_al + off_ctrl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);   // full[8], empty[8], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * kMaxStages + 4));
   float* s_bias = reinterpret_cast<float*>(ctrl + 1024);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
-  const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
-  const uint32_t bar_sfull = bar_tempty + 16, bar_sfree = bar_sfull + 64;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages, bar_tempty = bar_tfull + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_w);
-    if constexpr (MODE >= 1) tma_prefetch_desc(&tmap_d);
-    if constexpr (MODE == 2) tma_prefetch_desc(&tmap_r);
+    if constexpr (MODE == 1) tma_prefetch_desc(&tmap_d);
+    if (p.has_res) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
-    for (int s = 0; s < 8; s++) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sfree + 8 * s, 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+  if (p.has_res && warp >= kEpiWarp0) {
+    // 64x64 bf16 identity, K-major, SWIZZLE_128B: row n = 128 bytes, 16-byte chunk c stored at position c ^ (n & 7)
+    uint8_t* ident = smem_al + off_ident;
+    const int t = threadIdx.x - kEpiWarp0 * 32;
+    for (int i = t; i < kIdentBytes / 16; i += 128) reinterpret_cast<uint4*>(ident)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t < 64) {
+      const int n = t, c = n >> 3;
+      *reinterpret_cast<__nv_bfloat16*>(ident + n * 128 + ((c ^ (n & 7)) << 4) + (n & 7) * 2) = __float2bfloat16_rn(1.0f);
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -208,7 +224,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) {
     if (lane == 0) {  // ===================================== TMA producer
       uint32_t it = 0;
-      [[maybe_unused]] uint32_t gchunk = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
         for (int t = 0; t < p.taps; t++) {
@@ -216,18 +231,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
-            tma_load_2d(smem_a0 + s * Cfg::kStageBytesA, &tmap_a, bar_full + 8 * s, kb * BLOCK_K, m0 + p.shift[t]);
+            tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_a, bar_full + 8 * s, kb * BLOCK_K, m0 + p.shift[t]);
             tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * BLOCK_K, n0);
           }
         }
-        if constexpr (MODE == 2) {   // residual chunks of this tile -> slot ring (consumed and overwritten by the epilogue)
-          for (int c = 0; c < kChunksPerTile; c++) {
-            if (n0 + c * kSlotCols >= p.N) break;
-            const uint32_t s = gchunk % kSlots, ph = (gchunk / kSlots) & 1u;
-            mbar_wait(bar_sfree + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(bar_sfull + 8 * s, kSlotBytes);
-            tma_load_2d(smem_slot0 + s * kSlotBytes, &tmap_r, bar_sfull + 8 * s, n0 + c * kSlotCols, m0);
-            gchunk++;
+        if (p.has_res) {   // residual [128 x 64] tiles as extra A operands
+          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j++, it++) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytesA);
+            tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_r, bar_full + 8 * s, n0 + j * 64, m0);
           }
         }
       }
@@ -235,8 +248,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {  // ===================================== MMA issuer
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_res = make_idesc_bf16(BLOCK_M, 64);
+      const uint64_t ident_desc = make_smem_desc_sw128(smem_base + off_ident);
       uint32_t it = 0, tc = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
+        const int n0 = (tile % p.n_tiles) * BLOCK_N;
         const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
         mbar_wait(bar_tempty + 8 * b, bph ^ 1u);   // epilogue has drained this accumulator buffer
         tc_fence_after();
@@ -245,12 +261,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * Cfg::kStageBytesA);
+          const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * kStageBytesA);
           const uint64_t bdesc = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++)   // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);             // frees the smem slot once these MMAs have read it
+        }
+        if (p.has_res) {
+          if constexpr (BLOCK_N >= 64) {
+            for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j++, it++) {
+              const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+              mbar_wait(bar_full + 8 * s, ph);
+              tc_fence_after();
+              const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * kStageBytesA);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+                umma_bf16(tmem_d + j * 64, adesc + 2 * k, ident_desc + 2 * k, idesc_res, 1u);   // D[:, 64j:64j+64] += R_tile * I
+              umma_commit(bar_empty + 8 * s);
+            }
+          }
         }
         umma_commit(bar_tfull + 8 * b);               // accumulator complete -> epilogue
       }
@@ -260,14 +290,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int et = threadIdx.x - kEpiWarp0 * 32;      // 0..127 == row of the tile this thread owns
     constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;
     uint32_t tc = 0;
-    [[maybe_unused]] uint32_t gchunk = 0;             // running slot-ring position (MODE >= 1)
+    [[maybe_unused]] uint32_t gphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
       const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
       const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
-      // stage bias for this N tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if constexpr (MODE == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's bias reads are done
       for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if constexpr (MODE == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       const long long m = (long long)m0 + q * 32 + lane;
       bool zero_row = false;
       if (p.plane_h > 0) {
@@ -279,20 +308,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(bar_tfull + 8 * b, bph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BLOCK_N;
+      if constexpr (MODE == 0) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += CH) {
-        if (n0 + c >= p.N) break;                      // uniform: the rest of the tile lies beyond N
-        uint32_t v[32];
-        if constexpr (CH == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
-        float f[CH];
-#pragma unroll
-        for (int j = 0; j < CH; j++) f[j] = __uint_as_float(v[j]) + s_bias[c + j];
-        if constexpr (MODE == 0) {
+        for (int c = 0; c < BLOCK_N; c += CH) {
+          if (n0 + c >= p.N) break;                    // uniform: the rest of the tile lies beyond N
+          uint32_t v[32];
+          if constexpr (CH == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
           if (m < p.M) {
             const int ncols = (p.N - (n0 + c)) < CH ? (p.N - (n0 + c)) : CH;   // multiple of 8
+            float f[CH];
 #pragma unroll
             for (int j = 0; j < CH; j++) {
+              f[j] = __uint_as_float(v[j]) + s_bias[c + j];
               if (p.relu) f[j] = fmaxf(f[j], 0.f);
               if (zero_row) f[j] = 0.f;
             }
@@ -314,52 +342,54 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           }
-        } else {
-          // ---- slot ring: (residual arrives by TMA) -> add in place -> TMA store
-          const uint32_t s = gchunk % kSlots, ph = (gchunk / kSlots) & 1u;
-          uint8_t* slot = slot_ptr0 + s * kSlotBytes;
-          if constexpr (MODE == 2) mbar_wait(bar_sfull + 8 * s, ph);         // residual chunk has landed
-          else mbar_wait(bar_sfree + 8 * s, ph ^ 1u);                       // previous TMA store from this slot has drained
-          const int r = q * 32 + lane;
-          uint8_t* rowp = slot + r * 64;
-          const int sw = (r >> 1) & 3;                                       // SWIZZLE_64B: 16-byte chunk index ^= addr bits [7,9)
+        }
+      } else {
+        const int r = q * 32 + lane;
+        const int sw = r & 7;                           // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+#pragma unroll 1
+        for (int pc = 0; pc < BLOCK_N; pc += p.phase_cols) {
+          if (n0 + pc >= p.N) break;
+          const uint32_t buf_off = off_staging + (gphase & 1u) * (BLOCK_M * p.phase_cols * 2);
+          if (et == 0) tma_store_wait_read<1>();        // the TMA store issued two phases ago (this buffer) has read its smem
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+          for (int c = pc; c < pc + p.phase_cols; c += 32) {
+            if (n0 + c >= p.N) break;
+            uint32_t v[32];
+            tmem_ld32(taddr + c, v);
+            tmem_ld_wait();
+            // 64-column slot (16 KB, 128-byte rows) inside the phase buffer; this 32-column group is its low or high half
+            uint8_t* rowp = smem_al + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128) + r * 128;
+            const int half = ((c - pc) >> 5) & 1;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            uint4* cp = reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4));
-            if constexpr (MODE == 2) {
-              uint4 u = *cp;
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            for (int j = 0; j < 4; j++) {
+              uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-              for (int e = 0; e < 4; e++) { float2 r2 = __bfloat1622float2(h[e]); f[8 * j + 2 * e] += r2.x; f[8 * j + 2 * e + 1] += r2.y; }
+              for (int e = 0; e < 4; e++) {
+                float a0 = __uint_as_float(v[8 * j + 2 * e]) + s_bias[c + 8 * j + 2 * e];
+                float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + s_bias[c + 8 * j + 2 * e + 1];
+                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                if (zero_row) { a0 = 0.f; a1 = 0.f; }
+                ho[e] = __floats2bfloat162_rn(a0, a1);
+              }
+              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = o;
             }
-            uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              float a0 = f[8 * j + 2 * e], a1 = f[8 * j + 2 * e + 1];
-              if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-              if (zero_row) { a0 = 0.f; a1 = 0.f; }
-              ho[e] = __floats2bfloat162_rn(a0, a1);
-            }
-            *cp = o;
           }
-          fence_proxy_async();                                               // generic-proxy writes -> visible to the TMA store
+          fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (et == 0) {
-            tma_store_2d(&tmap_d, smem_slot0 + s * kSlotBytes, n0 + c, m0);  // rows >= M / cols >= N are clipped by the TMA unit
+            for (int c = pc; c < pc + p.phase_cols && n0 + c < p.N; c += 64)   // rows >= M / cols >= N are clipped by the TMA unit
+              tma_store_2d(&tmap_d, smem_base + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128), n0 + c, m0);
             tma_store_commit();
-            if (gchunk >= (uint32_t)Cfg::kStoreLag) {
-              tma_store_wait_read<Cfg::kStoreLag>();                         // store (gchunk - lag) has finished reading its slot
-              mbar_arrive(bar_sfree + 8 * ((gchunk - Cfg::kStoreLag) % kSlots));
-            }
           }
-          gchunk++;
+          gphase++;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
     }
-    if constexpr (MODE >= 1) {
+    if constexpr (MODE == 1) {
       if (et == 0) tma_store_wait_read<0>();          // smem must stay valid until the last stores have read it
     }
   }
@@ -402,45 +432,26 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, long long rows, long
   return 0;
 }
 
-// 2-D bf16 [rows, cols] map for the epilogue slot ring: box = [128 rows x 32 cols], 64-byte swizzle
-static int make_tmap_slot(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return set_error(LVCB200_EUNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kSlotCols, (cuuint32_t)BLOCK_M};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    snprintf(g_last_error, sizeof(g_last_error), "gemm: cuTensorMapEncodeTiled (slot) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
-    return LVCB200_EINVAL;
-  }
-  return 0;
-}
-
 template <int BLOCK_N, int MODE>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
                        cudaStream_t s) {
-  using Cfg = GemmCfg<BLOCK_N, MODE>;
-  static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
+  const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res);
+  if (smem > 232448) return set_error(LVCB200_EINVAL, "gemm: internal shared-memory budget exceeded");
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_bf16_tc_kernel<BLOCK_N, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tw, td, tr, p);
+  gemm_bf16_tc_kernel<BLOCK_N, MODE><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   return check_launch("gemm_bf16_tc_kernel");
 }
 
 template <int BLOCK_N>
 static int launch_gemm_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr,
                             const GemmParams& p, cudaStream_t s) {
-  if constexpr (BLOCK_N >= 32) {
-    if (mode == 2) return launch_gemm<BLOCK_N, 2>(ta, tw, td, tr, p, s);
+  if constexpr (BLOCK_N >= 64) {
     if (mode == 1) return launch_gemm<BLOCK_N, 1>(ta, tw, td, tr, p, s);
   }
   return launch_gemm<BLOCK_N, 0>(ta, tw, td, tr, p, s);
@@ -464,12 +475,11 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   LVC_REQUIRE(d->M < (1ll << 31) && d->M_rows < (1ll << 31), "gemm: M too large");
   int bn = d->N >= 256 ? 256 : (d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16)));
   if (d->N > 128 && d->N < 256) bn = 256;
-  // epilogue mode: fp32 output -> direct stores; bf16 output -> TMA-store slot ring (+ TMA-loaded residual)
-  int mode = d->d_dtype == LVCB200_F32 ? 0 : (d->residual ? 2 : 1);
-  if (mode != 0 && bn < 32) bn = 32;
-  LVC_REQUIRE(!(mode == 0 && d->residual), "gemm: residual with fp32 output is not supported");
+  // epilogue mode: fp32 output -> direct stores from registers; bf16 output -> smem staging + TMA stores
+  const int mode = d->d_dtype == LVCB200_F32 ? 0 : 1;
+  if ((mode == 1 || d->residual) && bn < 64) bn = 64;
   GemmParams p;
-  p.bias = d->bias; p.residual = (const __nv_bfloat16*)d->residual; p.ldr = d->ldr;
+  p.bias = d->bias;
   p.D = d->D; p.ldd = d->ldd; p.d_f32 = d->d_dtype == LVCB200_F32;
   p.M = d->M; p.N = d->N; p.K = d->K; p.taps = d->taps;
   for (int i = 0; i < 9; i++) p.shift[i] = i < d->taps ? d->shift[i] : 0;
@@ -477,14 +487,30 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   p.m_tiles = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
   p.n_tiles = (d->N + bn - 1) / bn;
   p.k_blocks = (d->K + BLOCK_K - 1) / BLOCK_K;
+  p.has_res = d->residual ? 1 : 0;
+  // smem split: deep operand pipeline for long K loops, shallow pipeline + wide staging when the epilogue dominates
+  const int k_iters = p.taps * p.k_blocks;
+  const int stage_bytes = kStageBytesA + bn * BLOCK_K * 2;
+  const bool deep = k_iters >= 12 && !p.has_res;
+  if (mode == 1) {
+    p.phase_cols = deep ? 64 : (bn >= 128 ? 128 : 64);
+    int budget = 232448 - (kCtrlBytes + 1024) - 2 * BLOCK_M * p.phase_cols * 2 - (p.has_res ? kIdentBytes : 0);
+    p.num_stages = budget / stage_bytes;
+  } else {
+    p.phase_cols = 64;
+    p.num_stages = (232448 - (kCtrlBytes + 1024) - (p.has_res ? kIdentBytes : 0)) / stage_bytes;
+  }
+  if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
+  if (!deep && p.num_stages > 4) p.num_stages = 4;
+  LVC_REQUIRE(p.num_stages >= 2, "gemm: internal: pipeline too shallow");
   CUtensorMap ta, tw, td, tr;
   int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M);
   if (rc) return rc;
   rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn);
   if (rc) return rc;
   td = ta; tr = ta;  // placeholders when unused (a valid map must still be passed by value)
-  if (mode >= 1 && (rc = make_tmap_slot(&td, d->D, d->M, d->N, d->ldd))) return rc;
-  if (mode == 2 && (rc = make_tmap_slot(&tr, d->residual, d->M, d->N, d->ldr))) return rc;
+  if (mode == 1 && (rc = make_tmap_2d(&td, d->D, d->M, d->N, d->ldd, BLOCK_M))) return rc;
+  if (p.has_res && (rc = make_tmap_2d(&tr, d->residual, d->M, d->N, d->ldr, BLOCK_M))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   switch (bn) {
     case 256: return launch_gemm_mode<256>(mode, ta, tw, td, tr, p, s);

@@ -146,13 +146,34 @@ template <> __device__ __forceinline__ void store_vec<__nv_bfloat16, 4>(__nv_bfl
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// 1-D bilinear footprint of one sample coordinate (the y or x half of bilinear_interpolate, ROIAlign_cuda.cu:12-62):
+// rows lo / hi with weights w_lo / w_hi; valid = inside [-1, size].
+struct Tap1 { int lo, hi; float wlo, whi; bool valid; };
+__device__ __forceinline__ Tap1 make_tap1(float y, int size) {
+  Tap1 t;
+  t.valid = !(y < -1.0f || y > (float)size);
+  if (y <= 0) y = 0;
+  int yl = (int)y, yh;
+  if (yl >= size - 1) { yh = yl = size - 1; y = (float)yl; } else yh = yl + 1;
+  float l = y - yl;
+  t.lo = yl; t.hi = yh; t.wlo = 1.f - l; t.whi = l;
+  return t;
+}
+
+constexpr int kMaxSepGrid = 16;
+
+// Bilinear weights are separable (w(y,x) = wy(y) * wx(x)) and the sample grid of a bin is a product grid, so
+//   sum_{iy,ix} sum_{corners} w * f  ==  sum_{rows} sum_{cols} Wy[row] * Wx[col] * f[row, col]
+// with Wy / Wx the per-row / per-column sums of the 1-D weights.  A bin with a g x g sample grid then reads (g+1)^2
+// pixel vectors instead of 4 g^2 -- the gather is L2-bandwidth bound, so this is the whole cost.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t R, int P, int sampling_ratio,
                     int canon_size, int canon_level, int min_level, TO* __restrict__ out, int out_layout,
                     int64_t out_pitch, int64_t* __restrict__ levels_out) {
   constexpr int V = Vec<TI>::N;
-  const int lane = threadIdx.x & 31;
+  __shared__ float sWy[8][kMaxSepGrid + 4], sWx[8][kMaxSepGrid + 4];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int bins = P * P;
@@ -171,24 +192,72 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
     const lvcb200_fmap fm = L.lv[lvl];
     const int H = fm.H, W = fm.W;
     RoiGeom g = roi_geom(roi, fm.spatial_scale, P, P, sampling_ratio, true);
+    const int gh = no_level ? 0 : g.grid_h, gw = no_level ? 0 : g.grid_w;
     const TI* base = reinterpret_cast<const TI*>(fm.base) + (int64_t)roi[0] * fm.img_stride * fm.c_stride;
+    const bool separable = gh >= 1 && gw >= 1 && gh <= kMaxSepGrid && gw <= kMaxSepGrid;
+    int ybase = 0, ny = 0, xbase = 0, nx = 0;
+    if (separable) {
+      const float y_first = g.start_h + ph * g.bin_h, x_first = g.start_w + pw * g.bin_w;
+      ybase = make_tap1(y_first + .5f * g.bin_h / (float)gh, H).lo;
+      ny = make_tap1(y_first + ((float)(gh - 1) + .5f) * g.bin_h / (float)gh, H).hi - ybase + 1;
+      xbase = make_tap1(x_first + .5f * g.bin_w / (float)gw, W).lo;
+      nx = make_tap1(x_first + ((float)(gw - 1) + .5f) * g.bin_w / (float)gw, W).hi - xbase + 1;
+      __syncwarp();
+      if (lane < ny) {
+        float wsum = 0.f;
+        for (int i = 0; i < gh; i++) {
+          Tap1 t = make_tap1(y_first + ((float)i + .5f) * g.bin_h / (float)gh, H);
+          if (!t.valid) continue;
+          if (t.lo == ybase + lane) wsum += t.wlo;
+          if (t.hi == ybase + lane) wsum += t.whi;
+        }
+        sWy[wib][lane] = wsum;
+      }
+      if (lane < nx) {
+        float wsum = 0.f;
+        for (int i = 0; i < gw; i++) {
+          Tap1 t = make_tap1(x_first + ((float)i + .5f) * g.bin_w / (float)gw, W);
+          if (!t.valid) continue;
+          if (t.lo == xbase + lane) wsum += t.wlo;
+          if (t.hi == xbase + lane) wsum += t.whi;
+        }
+        sWx[wib][lane] = wsum;
+      }
+      __syncwarp();
+    }
     for (int c0 = lane * V; c0 < C; c0 += 32 * V) {
       float acc[V];
 #pragma unroll
       for (int i = 0; i < V; i++) acc[i] = 0.f;
-      for (int iy = 0; iy < (no_level ? 0 : g.grid_h); iy++) {
-        float y = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
-        for (int ix = 0; ix < g.grid_w; ix++) {
-          float x = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
-          Tap t = make_tap(y, x, H, W);
-          if (!t.valid) continue;
-          float v1[V], v2[V], v3[V], v4[V];
-          Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x0) * fm.c_stride + c0, v1);
-          Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x1) * fm.c_stride + c0, v2);
-          Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x0) * fm.c_stride + c0, v3);
-          Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x1) * fm.c_stride + c0, v4);
+      if (separable) {
+        for (int ry = 0; ry < ny; ry++) {
+          const float wy = sWy[wib][ry];
+          if (wy == 0.f) continue;
+          const TI* rowp = base + ((int64_t)(ybase + ry) * fm.row_stride + xbase) * fm.c_stride + c0;
+          for (int rx = 0; rx < nx; rx++) {
+            const float w = wy * sWx[wib][rx];
+            if (w == 0.f) continue;
+            float v[V];
+            Vec<TI>::load(rowp + (int64_t)rx * fm.c_stride, v);
 #pragma unroll
-          for (int i = 0; i < V; i++) acc[i] += t.w1 * v1[i] + t.w2 * v2[i] + t.w3 * v3[i] + t.w4 * v4[i];
+            for (int i = 0; i < V; i++) acc[i] += w * v[i];
+          }
+        }
+      } else {
+        for (int iy = 0; iy < gh; iy++) {
+          float y = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
+          for (int ix = 0; ix < gw; ix++) {
+            float x = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
+            Tap t = make_tap(y, x, H, W);
+            if (!t.valid) continue;
+            float v1[V], v2[V], v3[V], v4[V];
+            Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x0) * fm.c_stride + c0, v1);
+            Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x1) * fm.c_stride + c0, v2);
+            Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x0) * fm.c_stride + c0, v3);
+            Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x1) * fm.c_stride + c0, v4);
+#pragma unroll
+            for (int i = 0; i < V; i++) acc[i] += t.w1 * v1[i] + t.w2 * v2[i] + t.w3 * v3[i] + t.w4 * v4[i];
+          }
         }
       }
 #pragma unroll
@@ -200,6 +269,7 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
         for (int i = 0; i < V; i++) out[r * out_pitch + (int64_t)(c0 + i) * bins + bin] = (TO)acc[i];
       }
     }
+    __syncwarp();
   }
 }
 

@@ -23,7 +23,7 @@ struct RpnLevels {
 
 struct RpnWs {  // element offsets inside the workspace (per (image, level) slot of kMaxTopk entries)
   size_t off_hdr, off_boxes, off_scores, off_valid, off_kboxes, off_kscores, off_kcount, off_hist1, off_hist2, off_ccount, off_cand,
-      zero_bytes, total;
+      off_mask, zero_bytes, total;
 };
 
 static RpnWs rpn_layout(int n_images, int n_levels) {
@@ -37,6 +37,7 @@ static RpnWs rpn_layout(int n_images, int n_levels) {
   w.off_ccount = take(slots * 4);
   w.zero_bytes = o;
   w.off_cand = take(slots * kCandCap * 8);
+  w.off_mask = take(slots * (size_t)kMaxTopk * (kMaxTopk / 64) * 8);
   w.off_boxes = take(slots * kMaxTopk * 16);
   w.off_scores = take(slots * kMaxTopk * 4);
   w.off_valid = take(slots * kMaxTopk);
@@ -315,33 +316,113 @@ rpn_select_decode_kernel(RpnLevels L, int n_levels, int topk, float min_box_size
   }
 }
 
-__global__ void __launch_bounds__(256)
-rpn_nms_kernel(int n_levels, int topk, float thr, int nms_mode, const float4* __restrict__ ws_boxes,
-               const float* __restrict__ ws_scores, const unsigned char* __restrict__ ws_valid, const uint32_t* __restrict__ hdr,
-               float4* __restrict__ k_boxes, float* __restrict__ k_scores, int* __restrict__ k_count) {
-  __shared__ NmsShared sh;
-  __shared__ float kx1[kMaxTopk], ky1[kMaxTopk], kx2[kMaxTopk], ky2[kMaxTopk], kar[kMaxTopk];
-  __shared__ unsigned char flags[kMaxTopk];
-  __shared__ int warp_cnt[8];
-  const int img = blockIdx.x / n_levels, lvl = blockIdx.x % n_levels;
-  const int slot0 = blockIdx.x * kMaxTopk;
+// ---- per-(image, level) NMS as suppression bit-matrix + in-smem sweep (n <= 1024):
+//   rpn_nms_mask_kernel : grid = slots x 136 upper-triangular 64x64 tile pairs, fully parallel IoU tests (same arithmetic as
+//                         nms_core.cuh / torchvision), mask[slot][i][w] bit j set <=> box j (> i, lower score) overlaps box i
+//   rpn_nms_sweep_kernel: CTA per slot: mask -> shared memory (128 KB), one warp resolves 64 candidates per step
+//                         (diagonal word: serial, branch-free; remaining words: lanes OR the rows of the kept boxes),
+//                         then ordered compaction of the kept boxes.  Greedy result == sequential NMS.
+constexpr int kMaskWords = kMaxTopk / 64;       // 16
+constexpr int kTilePairs = kMaskWords * (kMaskWords + 1) / 2;   // 136
+
+__global__ void __launch_bounds__(64)
+rpn_nms_mask_kernel(int n_levels, int topk, float thr, int nms_mode, const float4* __restrict__ ws_boxes,
+                    const unsigned char* __restrict__ ws_valid, const uint32_t* __restrict__ hdr, unsigned long long* __restrict__ mask) {
+  __shared__ float cx1[64], cy1[64], cx2[64], cy2[64], car[64];
+  __shared__ int cvalid[64];
+  const int slot = blockIdx.x / kTilePairs;
+  int pair = blockIdx.x - slot * kTilePairs, tr = 0;
+  while (pair >= kMaskWords - tr) { pair -= kMaskWords - tr; tr++; }
+  const int tc = tr + pair;
   const int n = topk < kMaxTopk ? topk : kMaxTopk;
+  if (tr * 64 >= n || tc * 64 >= n) return;
+  const int img = slot / n_levels, lvl = slot - img * n_levels;
   int mode = nms_mode;
   if (mode < 0) mode = reference_cuda_nms_mode((long long)hdr[img * 2 + 1]);
   const float off = (mode == 0) ? __fmul_rn((float)lvl, __fadd_rn(ordered_to_float(hdr[img * 2]), 1.0f)) : 0.f;
-  auto get = [&](int j, float& x1, float& y1, float& x2, float& y2) {
-    float4 b = ws_boxes[slot0 + j];
-    x1 = __fadd_rn(b.x, off); y1 = __fadd_rn(b.y, off); x2 = __fadd_rn(b.z, off); y2 = __fadd_rn(b.w, off);
-    return ws_valid[slot0 + j] != 0;
-  };
-  segment_nms(sh, get, n, thr, kx1, ky1, kx2, ky2, kar, flags);
+  const int t = threadIdx.x;
+  const int slot0 = slot * kMaxTopk;
+  {
+    const int j = tc * 64 + t;
+    float4 b = make_float4(0, 0, 0, 0); bool v = false;
+    if (j < n) { b = ws_boxes[slot0 + j]; v = ws_valid[slot0 + j] != 0; }
+    cx1[t] = __fadd_rn(b.x, off); cy1[t] = __fadd_rn(b.y, off); cx2[t] = __fadd_rn(b.z, off); cy2[t] = __fadd_rn(b.w, off);
+    car[t] = box_area(cx1[t], cy1[t], cx2[t], cy2[t]);
+    cvalid[t] = v ? 1 : 0;
+  }
   __syncthreads();
-  // ordered compaction of the kept (original, un-offset) boxes
+  const int i = tr * 64 + t;
+  unsigned long long bits = 0ull;
+  if (i < n && ws_valid[slot0 + i]) {
+    float4 b = ws_boxes[slot0 + i];
+    const float x1 = __fadd_rn(b.x, off), y1 = __fadd_rn(b.y, off), x2 = __fadd_rn(b.z, off), y2 = __fadd_rn(b.w, off);
+    const float ar = box_area(x1, y1, x2, y2);
+    const bool skip_zero = thr >= 0.f;
+    for (int jj = 0; jj < 64; jj++) {
+      const int j = tc * 64 + jj;
+      if (j <= i || !cvalid[jj]) continue;
+      if (skip_zero && (fminf(cx2[jj], x2) <= fmaxf(cx1[jj], x1) || fminf(cy2[jj], y2) <= fmaxf(cy1[jj], y1))) continue;
+      if (iou_gt(x1, y1, x2, y2, ar, cx1[jj], cy1[jj], cx2[jj], cy2[jj], car[jj], thr)) bits |= (1ull << jj);
+    }
+  }
+  if (i < n) mask[((size_t)slot0 + i) * kMaskWords + tc] = bits;
+}
+
+__global__ void __launch_bounds__(256)
+rpn_nms_sweep_kernel(int topk, const unsigned long long* __restrict__ mask, const float4* __restrict__ ws_boxes,
+                     const float* __restrict__ ws_scores, const unsigned char* __restrict__ ws_valid,
+                     float4* __restrict__ k_boxes, float* __restrict__ k_scores, int* __restrict__ k_count) {
+  extern __shared__ unsigned long long smask[];    // [n][16]
+  __shared__ unsigned long long validw[kMaskWords], keptw[kMaskWords];
+  __shared__ int warp_cnt[8];
+  const int slot0 = blockIdx.x * kMaxTopk;
+  const int n = topk < kMaxTopk ? topk : kMaxTopk;
+  const int nchunks = (n + 63) / 64;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(mask + (size_t)slot0 * kMaskWords);
+    uint4* dst = reinterpret_cast<uint4*>(smask);
+    for (int i = tid; i < n * kMaskWords / 2; i += blockDim.x) dst[i] = src[i];
+  }
+  if (tid < kMaskWords) validw[tid] = 0ull;
+  __syncthreads();
+  for (int j = tid; j < n; j += blockDim.x)
+    if (ws_valid[slot0 + j]) atomicOr(&validw[j >> 6], 1ull << (j & 63));
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long removed = 0ull;   // lane w (< 16) owns suppression word w
+    for (int c = 0; c < nchunks; c++) {
+      unsigned long long rc = __shfl_sync(0xffffffffu, removed, c);
+      unsigned long long kept = 0ull;
+      if (lane == 0) {
+        unsigned long long alive = validw[c] & ~rc;
+        const unsigned long long* diag = smask + (size_t)(c * 64) * kMaskWords + c;
+        const int rows = (n - c * 64) < 64 ? (n - c * 64) : 64;
+#pragma unroll 8
+        for (int i = 0; i < rows; i++) {
+          unsigned long long bit = (alive >> i) & 1ull;
+          kept |= bit << i;
+          alive &= ~(diag[(size_t)i * kMaskWords] & (0ull - bit));
+        }
+        keptw[c] = kept;
+      }
+      kept = __shfl_sync(0xffffffffu, kept, 0);
+      if (lane > c && lane < nchunks) {
+        unsigned long long k = kept;
+        while (k) {
+          int i = __ffsll((long long)k) - 1;
+          k &= k - 1;
+          removed |= smask[(size_t)(c * 64 + i) * kMaskWords + lane];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ordered compaction of the kept boxes
   int base = 0;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int j0 = 0; j0 < n; j0 += 256) {
-    int j = j0 + threadIdx.x;
-    bool kf = j < n && flags[j];
+    int j = j0 + tid;
+    bool kf = j < n && ((keptw[j >> 6] >> (j & 63)) & 1ull);
     unsigned int b = __ballot_sync(0xffffffffu, kf);
     if (lane == 0) warp_cnt[wid] = __popc(b);
     __syncthreads();
@@ -355,7 +436,7 @@ rpn_nms_kernel(int n_levels, int topk, float thr, int nms_mode, const float4* __
     base += tot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) k_count[blockIdx.x] = base;
+  if (tid == 0) k_count[blockIdx.x] = base;
 }
 
 __global__ void __launch_bounds__(256)
@@ -446,10 +527,22 @@ extern "C" int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels, const lvcb
                                                  (float*)(ws + w.off_scores), (unsigned char*)(ws + w.off_valid), hdr, ccount, cand);
   rc = check_launch("rpn_select_decode_kernel");
   if (rc) return rc;
-  rpn_nms_kernel<<<grid, 256, 0, s>>>(p->n_levels, p->pre_nms_topk, p->nms_thresh, p->nms_mode, (const float4*)(ws + w.off_boxes),
-                                      (const float*)(ws + w.off_scores), (const unsigned char*)(ws + w.off_valid), hdr,
-                                      (float4*)(ws + w.off_kboxes), (float*)(ws + w.off_kscores), (int*)(ws + w.off_kcount));
-  rc = check_launch("rpn_nms_kernel");
+  unsigned long long* mask = (unsigned long long*)(ws + w.off_mask);
+  rpn_nms_mask_kernel<<<grid * kTilePairs, 64, 0, s>>>(p->n_levels, p->pre_nms_topk, p->nms_thresh, p->nms_mode,
+                                                      (const float4*)(ws + w.off_boxes), (const unsigned char*)(ws + w.off_valid), hdr, mask);
+  if ((rc = check_launch("rpn_nms_mask_kernel"))) return rc;
+  {
+    static bool attr_set = false;
+    const int smem = kMaxTopk * kMaskWords * 8;
+    if (!attr_set) {
+      LVC_CUDA(cudaFuncSetAttribute(rpn_nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    rpn_nms_sweep_kernel<<<grid, 256, smem, s>>>(p->pre_nms_topk, mask, (const float4*)(ws + w.off_boxes), (const float*)(ws + w.off_scores),
+                                                 (const unsigned char*)(ws + w.off_valid), (float4*)(ws + w.off_kboxes),
+                                                 (float*)(ws + w.off_kscores), (int*)(ws + w.off_kcount));
+  }
+  rc = check_launch("rpn_nms_sweep_kernel");
   if (rc) return rc;
   rpn_merge_kernel<<<p->n_images, 256, 0, s>>>(p->n_levels, p->post_nms_topk, (const float4*)(ws + w.off_kboxes),
                                                (const float*)(ws + w.off_kscores), (const int*)(ws + w.off_kcount),

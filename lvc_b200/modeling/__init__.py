@@ -1,4 +1,5 @@
+from .corrector import BoxCorrectorHead
 from .engine import DetectorEngine
 from .rcnn import GeneralizedRCNN
 
-__all__ = ["DetectorEngine", "GeneralizedRCNN"]
+__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN"]

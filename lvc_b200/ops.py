@@ -183,6 +183,19 @@ def detections(cls_logits, box_deltas, proposals, roi_image, image_sizes, out_si
     return boxes, scores, classes, rows, counts
 
 
+def apply_deltas_clip(boxes, deltas, weights, roi_image=None, image_sizes=None):
+    """Class-agnostic Box2BoxTransform.apply_deltas (+ Boxes.clip when roi_image / image_sizes are given)."""
+    _lib.require_cuda(boxes, deltas, roi_image, image_sizes)
+    assert boxes.dtype == torch.float32 and deltas.dtype == torch.float32 and deltas.stride(1) == 1
+    boxes = boxes.contiguous()
+    out = torch.empty_like(boxes)
+    w = (ctypes.c_float * 4)(*weights)
+    rc = _lib.load().lvcb200_apply_deltas_clip(_lib.ptr(boxes), _lib.ptr(deltas), deltas.stride(0), _lib.ptr(roi_image), _lib.ptr(image_sizes),
+                                               boxes.shape[0], w, int(roi_image is not None), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lvcb200_apply_deltas_clip")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- kNN
 class KnnBank:
     """Support bank after the all-gather: centred + normalised once (lvcb200_knn_prepare)."""

@@ -48,6 +48,12 @@ def test_gemm_residual_relu_and_pitches():
     ops.gemm(a, w, residual=res, relu=True, out=dbuf[:, :N])
     _close(dbuf[:, :N], torch.relu(_ref_mm(a, w) + res.float()), True)
     assert float((dbuf[:, N:] - 7.0).abs().max()) == 0.0                 # nothing written outside D
+    # residual with fp32 output and a partial last N tile (residual rides the tensor core as an identity-MMA K step)
+    N2 = 416
+    w3 = (torch.randn(N2, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    res3 = torch.randn(M, N2, generator=g).bfloat16().to(DEV)
+    _close(ops.gemm(a, w3, residual=res3, out_dtype=torch.float32), _ref_mm(a, w3) + res3.float(), False)
+    _close(ops.gemm(a, w3, residual=res3, relu=True), torch.relu(_ref_mm(a, w3) + res3.float()), True)
     # K not a multiple of 64 (single tap): TMA zero-fills the tail of the last K block
     a2 = torch.randn(M, 152, generator=g).bfloat16().to(DEV)
     w2 = torch.randn(N, 152, generator=g).bfloat16().to(DEV)

@@ -165,3 +165,32 @@ def test_uint8_images_match_float_images():
     torch.cuda.synchronize()
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_box_corrector_vs_golden_and_oracle(golden):
+    """a17: 3-stage box corrector against the reference's CascadeROIHeads._forward_box_qe output (fp32 golden; bf16 engine ->
+    boxes within 0.5 px) and against the bf16-emulating oracle fed the same rounded features (tight)."""
+    from lvc_b200 import ops
+    from lvc_b200.modeling import BoxCorrectorHead
+    from lvc_b200.weights import synthetic_corrector_head
+    g = golden("box_corrector")
+    cfg = DetectorConfig(depth=50, num_fc=3)
+    sd = synthetic_corrector_head(cfg, seed=int(g["seed_head"]))
+    for k in list(sd):
+        if "bbox_pred.weight" in k:
+            sd[k] = sd[k] * float(g["scale"])
+    feats = {l: torch.from_numpy(g[f"feat_p{l}"].astype(np.float32)) for l in (2, 3, 4, 5)}
+    planes = [ops.Plane.from_nchw(feats[l].cuda()) for l in (2, 3, 4, 5)]
+    sizes = [tuple(int(v) for v in s) for s in g["image_sizes"]]
+    head = BoxCorrectorHead(cfg, sd)
+    out = head(planes, [torch.from_numpy(g["boxes0"]).cuda()], sizes)
+    got = out[0].cpu().numpy()
+    assert np.abs(got - g["boxes0"]).max() > 0.5                       # the head moved the boxes
+    assert np.abs(got - g["out_boxes0"]).max() < 0.5                   # vs the reference's fp32 result (bf16 features / weights)
+    OM._EMULATE_BF16 = True
+    try:
+        ref = OM.box_corrector_forward(cfg, sd, {f"p{l}": feats[l].bfloat16().float() for l in (2, 3, 4, 5)}, [g["boxes0"]],
+                                       [g["classes0"]], sizes)
+    finally:
+        OM._EMULATE_BF16 = False
+    assert np.abs(got - ref[0]).max() < 0.1
