@@ -21,7 +21,8 @@ namespace lvcb200 {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue (two per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -197,11 +198,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+    for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, kEpiThreads / 32); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
-  if (p.has_res && warp >= kEpiWarp0) {
+  if (p.has_res && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // 64x64 bf16 identity, K-major, SWIZZLE_128B: row n = 128 bytes, 16-byte chunk c stored at position c ^ (n & 7)
     uint8_t* ident = smem_al + off_ident;
     const int t = threadIdx.x - kEpiWarp0 * 32;
@@ -285,18 +286,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         umma_commit(bar_tfull + 8 * b);               // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= kEpiWarp0) {  // ========================= epilogue warps
+  } else if (warp >= kEpiWarp0) {  // ========================= epilogue warps (8: two per TMEM lane quadrant, split by columns)
     const int q = warp & 3;                           // TMEM lane quadrant this warp may access
-    const int et = threadIdx.x - kEpiWarp0 * 32;      // 0..127 == row of the tile this thread owns
+    const int half = (warp - kEpiWarp0) >> 2;         // which half of the columns of a phase / chunk pair this warp handles
+    const int et = threadIdx.x - kEpiWarp0 * 32;      // 0..255
     constexpr int CH = BLOCK_N < 32 ? BLOCK_N : 32;
     uint32_t tc = 0;
     [[maybe_unused]] uint32_t gphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
       const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
       const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
-      if constexpr (MODE == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's bias reads are done
-      for (int j = et; j < BLOCK_N; j += 128) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-      if constexpr (MODE == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      if constexpr (MODE == 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's bias reads are done
+      for (int j = et; j < BLOCK_N; j += kEpiThreads) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      if constexpr (MODE == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       const long long m = (long long)m0 + q * 32 + lane;
       bool zero_row = false;
       if (p.plane_h > 0) {
@@ -310,8 +312,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BLOCK_N;
       if constexpr (MODE == 0) {
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += CH) {
-          if (n0 + c >= p.N) break;                    // uniform: the rest of the tile lies beyond N
+        for (int c = half * CH; c < BLOCK_N; c += 2 * CH) {
+          if (n0 + c >= p.N) break;                    // the rest of this warp's chunks lie beyond N
           uint32_t v[32];
           if constexpr (CH == 32) tmem_ld32(taddr + c, v); else tmem_ld16(taddr + c, v);
           tmem_ld_wait();
@@ -346,37 +348,46 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       } else {
         const int r = q * 32 + lane;
         const int sw = r & 7;                           // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+        const int cols_per_warp = p.phase_cols >> 1;    // 32 (phase 64) or 64 (phase 128)
 #pragma unroll 1
         for (int pc = 0; pc < BLOCK_N; pc += p.phase_cols) {
           if (n0 + pc >= p.N) break;
           const uint32_t buf_off = off_staging + (gphase & 1u) * (BLOCK_M * p.phase_cols * 2);
           if (et == 0) tma_store_wait_read<1>();        // the TMA store issued two phases ago (this buffer) has read its smem
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
-          for (int c = pc; c < pc + p.phase_cols; c += 32) {
-            if (n0 + c >= p.N) break;
-            uint32_t v[32];
-            tmem_ld32(taddr + c, v);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int c0 = pc + half * cols_per_warp;     // this warp's columns of the phase: [c0, c0 + cols_per_warp)
+          if (n0 + c0 < p.N) {
+            uint32_t v[64];
+            tmem_ld32(taddr + c0, v);
+            if (cols_per_warp == 64) tmem_ld32(taddr + c0 + 32, v + 32);
             tmem_ld_wait();
-            // 64-column slot (16 KB, 128-byte rows) inside the phase buffer; this 32-column group is its low or high half
-            uint8_t* rowp = smem_al + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128) + r * 128;
-            const int half = ((c - pc) >> 5) & 1;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+            for (int g2 = 0; g2 < 2; g2++) {
+              if (g2 * 32 >= cols_per_warp) break;
+              const int c = c0 + g2 * 32;
+              // 64-column slot (16 KB, 128-byte rows) inside the phase buffer; this 32-column group is its low or high half
+              uint8_t* rowp = smem_al + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128) + r * 128;
+              const int hs = ((c - pc) >> 5) & 1;
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                float a0 = __uint_as_float(v[8 * j + 2 * e]) + s_bias[c + 8 * j + 2 * e];
-                float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + s_bias[c + 8 * j + 2 * e + 1];
-                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                if (zero_row) { a0 = 0.f; a1 = 0.f; }
-                ho[e] = __floats2bfloat162_rn(a0, a1);
+              for (int j = 0; j < 4; j++) {
+                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c + 8 * j);
+                const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 8 * j + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  float a0 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e]) + bb[2 * e];
+                  float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
+                  if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                  if (zero_row) { a0 = 0.f; a1 = 0.f; }
+                  ho[e] = __floats2bfloat162_rn(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(rowp + (((hs * 4 + j) ^ sw) << 4)) = o;
               }
-              *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = o;
             }
           }
           fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (et == 0) {
             for (int c = pc; c < pc + p.phase_cols && n0 + c < p.N; c += 64)   // rows >= M / cols >= N are clipped by the TMA unit
               tma_store_2d(&tmap_d, smem_base + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128), n0 + c, m0);

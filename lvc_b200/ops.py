@@ -10,6 +10,15 @@ from ._lib import BF16, F32, OUT_NCHW, OUT_NHWC, DetParams, FMap, GemmDesc, RpnL
 
 _ws = {}
 GEMM_EVENTS = None   # bench.py sets this to a list to time every GEMM launch with CUDA events on the launch stream
+GEMM_RECORD = None   # bench.py sets this to a list to record every GEMM descriptor of a step (replayed alone inside a CUDA graph)
+
+
+def replay_gemms(descs):
+    """Re-issue recorded GEMM launches (same buffers) on the current stream; used to time the dense layers back to back."""
+    lib = _lib.load()
+    sp = _lib.stream_ptr()
+    for d, _ in descs:
+        _lib.check(lib.lvcb200_gemm_bf16(ctypes.byref(d), sp), "lvcb200_gemm_bf16")
 
 
 def _workspace(tag, nbytes, device):
@@ -251,6 +260,8 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
         d.shift[i] = int(s)
     d.relu = int(relu)
     d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
+    if GEMM_RECORD is not None:
+        GEMM_RECORD.append((d, (A, W, bias, residual, out)))   # keep the tensors alive with the descriptor
     if GEMM_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
