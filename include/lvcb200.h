@@ -66,6 +66,7 @@ typedef struct {
 
 #define LVCB200_F32 0
 #define LVCB200_BF16 1
+#define LVCB200_F16 3
 #define LVCB200_OUT_NCHW 0 /* [R, C, ph, pw]  (reference order; fc1 weight index c*49+h*7+w) */
 #define LVCB200_OUT_NHWC 1 /* [R, ph, pw, C]  (engine order; fc1 weight permuted at load time) */
 
@@ -175,6 +176,13 @@ int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_prepared, vo
 int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
                        const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
                        int64_t* votes, uint8_t* keep, void* stream);
+/* Same contract and the same (exact fp32) results, with the Q x S x D contraction on the tensor cores: TF32 scores straight
+ * from the fp32 queries, a rigorous error bound selects a candidate superset per query, candidates are re-scored exactly.
+ * Needs 64 <= S <= 4096, D % 8 == 0, and a device workspace of lvcb200_knn_tc_workspace(Q, S) bytes. */
+size_t lvcb200_knn_tc_workspace(int64_t Q, int S);
+int lvcb200_knn_verify_tc(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
+                          const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
+                          int64_t* votes, uint8_t* keep, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Dense layers: tcgen05 / TMEM / TMA GEMM with row-shifted A operands ("shift-GEMM"), which is how the
@@ -191,11 +199,12 @@ int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank_cls, int S
  * extents; rows are n*plane_h*plane_w + y*plane_w + x) so the result is again a valid zero-bordered plane.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct {
+  int a_dtype;                                  /* LVCB200_BF16; or LVCB200_F32: A and W are fp32, multiplied as TF32 (kNN scores) */
   const void* A; int64_t lda; int64_t M_rows;   /* rows addressable in A (TMA bound) */
   const void* W; int64_t ldw;                   /* [N, taps*K] */
   const float* bias;                            /* [N] fp32 or NULL */
   const void* residual; int64_t ldr;            /* bf16 [M, N] or NULL (added before activation) */
-  void* D; int64_t ldd; int d_dtype;            /* LVCB200_BF16 or LVCB200_F32 */
+  void* D; int64_t ldd; int d_dtype;            /* LVCB200_BF16, LVCB200_F16 or LVCB200_F32 */
   int64_t M; int N; int K;                      /* GEMM extents (K per tap), K % 64 == 0, N % 16 == 0 */
   int taps; int32_t shift[9];                   /* row shift per tap */
   int relu;

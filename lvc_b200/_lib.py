@@ -10,7 +10,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblvcb200.so")
 
-F32, BF16, U8 = 0, 1, 2
+F32, BF16, U8, F16 = 0, 1, 2, 3
 OUT_NCHW, OUT_NHWC = 0, 1
 
 
@@ -38,7 +38,7 @@ class DetParams(Structure):
 
 
 class GemmDesc(Structure):
-    _fields_ = [("A", c_void_p), ("lda", c_int64), ("M_rows", c_int64), ("W", c_void_p), ("ldw", c_int64),
+    _fields_ = [("a_dtype", c_int), ("A", c_void_p), ("lda", c_int64), ("M_rows", c_int64), ("W", c_void_p), ("ldw", c_int64),
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64), ("D", c_void_p), ("ldd", c_int64),
                 ("d_dtype", c_int), ("M", c_int64), ("N", c_int), ("K", c_int), ("taps", c_int), ("shift", c_int32 * 9),
                 ("relu", c_int), ("plane_h", c_int), ("plane_w", c_int)]
@@ -69,6 +69,9 @@ _SIGS = {
     "lvcb200_knn_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_knn_verify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lvcb200_knn_tc_workspace": (c_size_t, [c_int64, c_int]),
+    "lvcb200_knn_verify_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lvcb200_gemm_bf16": (c_int, [POINTER(GemmDesc), c_void_p]),
     "lvcb200_stem_s2d4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_maxpool_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -13,6 +13,7 @@
 // warps 4..7 epilogue (TMEM lane quadrant = warp % 4).  Two TMEM accumulator buffers let the epilogue of tile i
 // overlap the main loop of tile i+1.  Tile = 128 x BLOCK_N, BLOCK_K = 64 (one 128-byte swizzle row).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -96,6 +97,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, fp32 operands in shared memory consumed as TF32 (10-bit mantissa), K = 8 per instruction
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -131,11 +138,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::tf32: A/B format field = 2 (TF32)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 struct GemmParams {
   const float* bias;
-  void* D; long long ldd; int d_f32;
+  void* D; long long ldd; int d_f32; int d_f16;
   long long M; int N; int K;
+  int k_elems;                     // operand elements per 128-byte K block: 64 (bf16) or 32 (fp32 consumed as tf32)
   int taps; int shift[9];
   int relu;
   int plane_h, plane_w;
@@ -168,7 +180,7 @@ __host__ __device__ inline int gemm_smem_bytes(int block_n, int mode, int num_st
   return b + kCtrlBytes + 1024 /*alignment slack*/;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int KIND>   // KIND 0: bf16 operands (kind::f16); KIND 1: fp32 operands as tf32 (kind::tf32)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -232,8 +244,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
-            tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_a, bar_full + 8 * s, kb * BLOCK_K, m0 + p.shift[t]);
-            tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * BLOCK_K, n0);
+            tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_a, bar_full + 8 * s, kb * p.k_elems, m0 + p.shift[t]);
+            tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * p.k_elems, n0);
           }
         }
         if (p.has_res) {   // residual [128 x 64] tiles as extra A operands
@@ -248,7 +260,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===================================== MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = KIND == 1 ? make_idesc_tf32(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M, BLOCK_N);
       constexpr uint32_t idesc_res = make_idesc_bf16(BLOCK_M, 64);
       const uint64_t ident_desc = make_smem_desc_sw128(smem_base + off_ident);
       uint32_t it = 0, tc = 0;
@@ -265,8 +277,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * kStageBytesA);
           const uint64_t bdesc = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; k++)   // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {  // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
+            if constexpr (KIND == 1) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(bar_empty + 8 * s);             // frees the smem slot once these MMAs have read it
         }
         if (p.has_res) {
@@ -380,7 +394,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
                   if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
                   if (zero_row) { a0 = 0.f; a1 = 0.f; }
-                  ho[e] = __floats2bfloat162_rn(a0, a1);
+                  if (p.d_f16) { __half2 hh = __floats2half2_rn(a0, a1); ho[e] = *reinterpret_cast<__nv_bfloat162*>(&hh); }
+                  else ho[e] = __floats2bfloat162_rn(a0, a1);
                 }
                 *reinterpret_cast<uint4*>(rowp + (((hs * 4 + j) ^ sw) << 4)) = o;
               }
@@ -426,14 +441,15 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows x 64 cols], 128-byte swizzle
-static int make_tmap_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+static int make_tmap_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                        bool f32 = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(LVCB200_EUNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : BLOCK_K), (cuuint32_t)box_rows};   // 128-byte inner box either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -443,19 +459,19 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, long long rows, long
   return 0;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int KIND = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
                        cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res);
   if (smem > 232448) return set_error(LVCB200_EINVAL, "gemm: internal shared-memory budget exceeded");
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_bf16_tc_kernel<BLOCK_N, MODE><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+  gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   return check_launch("gemm_bf16_tc_kernel");
 }
 
@@ -478,26 +494,31 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (d->M == 0) return 0;
   LVC_REQUIRE(d->A && d->W && d->D, "gemm: NULL pointer");
   LVC_REQUIRE(d->N % 8 == 0, "gemm: N must be a multiple of 8");
+  const bool tf32 = d->a_dtype == LVCB200_F32;   // fp32 operands consumed by the tensor core as TF32
+  LVC_REQUIRE(d->a_dtype == LVCB200_BF16 || tf32, "gemm: a_dtype must be LVCB200_BF16 or LVCB200_F32");
+  LVC_REQUIRE(!tf32 || (d->taps == 1 && !d->residual && d->d_dtype != LVCB200_F32 && d->N >= 64), "gemm: tf32 path: single tap, no residual, 16-bit output, N >= 64");
   LVC_REQUIRE(d->K % 8 == 0 && (d->taps == 1 || d->K % BLOCK_K == 0), "gemm: K must be a multiple of 8 (64 when taps > 1)");
-  LVC_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0, "gemm: lda / ldw must be multiples of 8 elements (16 bytes)");
+  LVC_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0, "gemm: lda / ldw must be multiples of 8 elements");
   LVC_REQUIRE(((uintptr_t)d->A % 16) == 0 && ((uintptr_t)d->W % 16) == 0 && ((uintptr_t)d->D % 16) == 0, "gemm: pointers must be 16-byte aligned");
   LVC_REQUIRE(d->ldd % (d->d_dtype == LVCB200_F32 ? 4 : 8) == 0, "gemm: ldd alignment");
   LVC_REQUIRE(!d->residual || (d->ldr % 8 == 0 && ((uintptr_t)d->residual % 16) == 0), "gemm: residual alignment");
   LVC_REQUIRE(d->M < (1ll << 31) && d->M_rows < (1ll << 31), "gemm: M too large");
   int bn = d->N >= 256 ? 256 : (d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16)));
   if (d->N > 128 && d->N < 256) bn = 256;
+  if (tf32) bn = ((d->N + 127) / 128 * 128 < (d->N + 255) / 256 * 256) ? 128 : 256;   // less column padding wins
   // epilogue mode: fp32 output -> direct stores from registers; bf16 output -> smem staging + TMA stores
   const int mode = d->d_dtype == LVCB200_F32 ? 0 : 1;
   if ((mode == 1 || d->residual) && bn < 64) bn = 64;
   GemmParams p;
   p.bias = d->bias;
-  p.D = d->D; p.ldd = d->ldd; p.d_f32 = d->d_dtype == LVCB200_F32;
+  p.D = d->D; p.ldd = d->ldd; p.d_f32 = d->d_dtype == LVCB200_F32; p.d_f16 = d->d_dtype == LVCB200_F16;
+  p.k_elems = tf32 ? 32 : BLOCK_K;
   p.M = d->M; p.N = d->N; p.K = d->K; p.taps = d->taps;
   for (int i = 0; i < 9; i++) p.shift[i] = i < d->taps ? d->shift[i] : 0;
   p.relu = d->relu; p.plane_h = d->plane_h; p.plane_w = d->plane_w;
   p.m_tiles = (int)((d->M + BLOCK_M - 1) / BLOCK_M);
   p.n_tiles = (d->N + bn - 1) / bn;
-  p.k_blocks = (d->K + BLOCK_K - 1) / BLOCK_K;
+  p.k_blocks = (d->K + p.k_elems - 1) / p.k_elems;
   p.has_res = d->residual ? 1 : 0;
   // smem split: deep operand pipeline for long K loops, shallow pipeline + wide staging when the epilogue dominates
   const int k_iters = p.taps * p.k_blocks;
@@ -515,14 +536,15 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (!deep && p.num_stages > 4) p.num_stages = 4;
   LVC_REQUIRE(p.num_stages >= 2, "gemm: internal: pipeline too shallow");
   CUtensorMap ta, tw, td, tr;
-  int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M);
+  int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M, tf32);
   if (rc) return rc;
-  rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn);
+  rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn, tf32);
   if (rc) return rc;
   td = ta; tr = ta;  // placeholders when unused (a valid map must still be passed by value)
   if (mode == 1 && (rc = make_tmap_2d(&td, d->D, d->M, d->N, d->ldd, BLOCK_M))) return rc;
   if (p.has_res && (rc = make_tmap_2d(&tr, d->residual, d->M, d->N, d->ldr, BLOCK_M))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if (tf32) return bn == 256 ? launch_gemm<256, 1, 1>(ta, tw, td, tr, p, s) : launch_gemm<128, 1, 1>(ta, tw, td, tr, p, s);
   switch (bn) {
     case 256: return launch_gemm_mode<256>(mode, ta, tw, td, tr, p, s);
     case 128: return launch_gemm_mode<128>(mode, ta, tw, td, tr, p, s);

@@ -3,7 +3,16 @@
 //                clamp of the norm at eps = 1e-8), done once after the support bank is gathered.
 //   knn_verify : CTA per 32 queries; centred query tile and bank tile staged in shared memory, 4x4 register
 //                tiles, fp32 FMA; running top-k per query in shared memory; votes / mode / keep fused at the end.
-// Round-1 kernel is fp32 SIMT (exact-arithmetic friendly); the tcgen05 path for the contraction is planned.
+// Two paths:
+//   exact SIMT (knn_verify_kernel)  : fp32 FMA, any S <= 4096; also the fallback of the tensor-core path.
+//   tensor core (lvcb200_knn_verify_tc): (1) approximate scores (q . bhat_s - mu . bhat_s) for all (query, bank row) pairs with the
+//       tcgen05 shift-GEMM in kind::tf32 straight from the fp32 queries (gemm_tc.cu), fp16 out; (2) knn_rerank_kernel, warp per
+//       query: rigorous candidate set {s : approx_s >= (k-th largest approx) - 2 eps}, eps bounding TF32 + fp16 rounding by
+//       Cauchy-Schwarz, then EXACT fp32 centred-cosine re-scoring of the candidates, top-k, votes, mode, keep.  The result is
+//       the exact fp32 top-k (not a TF32 approximation); queries whose candidate set overflows are redone by the SIMT kernel.
+#include <cuda_fp16.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace lvcb200 {
@@ -19,9 +28,16 @@ __global__ void knn_mean_kernel(const float* __restrict__ bank, int S, int D, fl
 }
 
 __global__ void __launch_bounds__(256)
-knn_normalize_kernel(const float* __restrict__ bank, int D, const float* __restrict__ mean, float* __restrict__ bhat) {
+knn_normalize_kernel(const float* __restrict__ bank, int S, int D, const float* __restrict__ mean, float* __restrict__ bhat,
+                     float* __restrict__ negc) {
   const int s = blockIdx.x;
+  if (s >= S) {   // zero padding rows (the score GEMM reads S rounded up to a multiple of 8)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) bhat[(size_t)s * D + d] = 0.f;
+    if (threadIdx.x == 0) negc[s] = 0.f;
+    return;
+  }
   __shared__ double red[8];
+  __shared__ double red2[8];
   __shared__ float s_inv;
   double a = 0.0;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -38,14 +54,23 @@ knn_normalize_kernel(const float* __restrict__ bank, int D, const float* __restr
   }
   __syncthreads();
   const float nrm = s_inv;
-  for (int d = threadIdx.x; d < D; d += blockDim.x)
-    bhat[(size_t)s * D + d] = __fdiv_rn(__fsub_rn(bank[(size_t)s * D + d], mean[d]), nrm);
+  double c = 0.0;   // c_s = mu . bhat_s  (so that q . bhat_s - c_s == (q - mu) . bhat_s)
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v = __fdiv_rn(__fsub_rn(bank[(size_t)s * D + d], mean[d]), nrm);
+    bhat[(size_t)s * D + d] = v;
+    c += (double)v * (double)mean[d];
+  }
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) red2[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < 8; i++) t += red2[i]; negc[s] = (float)(-t); }
 }
 
 __global__ void __launch_bounds__(256)
 knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat, const int64_t* __restrict__ bank_cls, int S, int D,
                   const float* __restrict__ queries, const int64_t* __restrict__ query_cls, int64_t Q, int topk, int knn,
-                  int64_t* __restrict__ top_idx, float* __restrict__ top_sim, int64_t* __restrict__ votes, uint8_t* __restrict__ keep) {
+                  int64_t* __restrict__ top_idx, float* __restrict__ top_sim, int64_t* __restrict__ votes, uint8_t* __restrict__ keep,
+                  const uint8_t* __restrict__ only_flagged) {
   __shared__ __align__(16) float As[KT][QT];
   __shared__ __align__(16) float Bs[KT][BT];
   __shared__ float Ss[QT][BT + 1];
@@ -54,6 +79,11 @@ knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
   __shared__ int tk_idx[QT][KNN_MAXK];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int64_t q0 = (int64_t)blockIdx.x * QT;
+  if (only_flagged != nullptr) {   // fallback pass of the tensor-core path: skip tiles without an overflowed query
+    int any = 0;
+    if (tid < QT && q0 + tid < Q) any = only_flagged[q0 + tid];
+    if (!__syncthreads_or(any)) return;
+  }
   if (tid < QT) for (int k = 0; k < KNN_MAXK; k++) { tk_sim[tid][k] = -INFINITY; tk_idx[tid][k] = -1; }
   const int lq = tid >> 3, lk = (tid & 7) * 4;  // loader mapping for the query tile
   float qss = 0.f;                              // partial sum of squares of the centred query (first bank tile only)
@@ -121,7 +151,7 @@ knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
     }
     __syncthreads();
   }
-  if (tid < QT && q0 + tid < Q) {
+  if (tid < QT && q0 + tid < Q && (only_flagged == nullptr || only_flagged[q0 + tid])) {
     const int64_t q = q0 + tid;
     int64_t v[KNN_MAXK];
     for (int k = 0; k < topk; k++) {
@@ -142,22 +172,147 @@ knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
   }
 }
 
+
+constexpr int RR_WARPS = 4;
+constexpr int RR_CAND = 96;
+
+// warp per query; dynamic smem per warp: S_pad halfs (scores) + D floats (centred query) + candidate arrays
+__global__ void __launch_bounds__(RR_WARPS * 32)
+knn_rerank_kernel(const float* __restrict__ mean, const float* __restrict__ bhat, const int64_t* __restrict__ bank_cls, int S, int S_pad,
+                  int D, const float* __restrict__ queries, const int64_t* __restrict__ query_cls, int64_t Q,
+                  const __half* __restrict__ scores, int topk, int knn, int64_t* __restrict__ top_idx, float* __restrict__ top_sim,
+                  int64_t* __restrict__ votes, uint8_t* __restrict__ keep, uint8_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t per_warp = (size_t)S_pad * 2 + (size_t)D * 4 + RR_CAND * 8;
+  unsigned char* base = rr_smem + w * ((per_warp + 15) / 16 * 16);
+  __half* ssc = reinterpret_cast<__half*>(base);
+  float* qc = reinterpret_cast<float*>(base + (((size_t)S_pad * 2 + 15) / 16 * 16));
+  int* cidx = reinterpret_cast<int*>(qc + D);
+  float* csim = reinterpret_cast<float*>(cidx + RR_CAND);
+  for (int64_t q = (int64_t)blockIdx.x * RR_WARPS + w; q < Q; q += (int64_t)gridDim.x * RR_WARPS) {
+    __syncwarp();
+    // (a) approximate scores of this query -> smem
+    const uint4* srow = reinterpret_cast<const uint4*>(scores + q * S_pad);
+    for (int i = lane; i < S_pad / 8; i += 32) reinterpret_cast<uint4*>(ssc)[i] = __ldg(srow + i);
+    // (b) centred query -> smem, norms
+    float nq = 0.f, nqc = 0.f;
+    for (int k = lane * 4; k < D; k += 128) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(queries + q * D + k));
+      float4 m = __ldg(reinterpret_cast<const float4*>(mean + k));
+      nq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      v.x = __fsub_rn(v.x, m.x); v.y = __fsub_rn(v.y, m.y); v.z = __fsub_rn(v.z, m.z); v.w = __fsub_rn(v.w, m.w);
+      nqc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      *reinterpret_cast<float4*>(qc + k) = v;
+    }
+    for (int o = 16; o; o >>= 1) { nq += __shfl_xor_sync(0xffffffffu, nq, o); nqc += __shfl_xor_sync(0xffffffffu, nqc, o); }
+    const float norm_q = sqrtf(nq), norm_qc = sqrtf(nqc);
+    // rigorous error bound of an approximate score: TF32 operand rounding (2^-10 each) by Cauchy-Schwarz with |bhat| <= 1,
+    // fp32 accumulation, fp16 output rounding (2^-11 |score|, |score| <= |q - mu|); 30 % slack
+    const float eps = 0.0026f * norm_q + 0.0007f * norm_qc + 1e-6f;
+    __syncwarp();
+    // (c) k-th largest approximate score: k rounds of "next element in (value desc, index asc) order"
+    float cur_v = INFINITY; int cur_i = -1;
+    for (int round = 0; round < topk; round++) {
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int i = lane; i < S; i += 32) {
+        float v = __half2float(ssc[i]);
+        bool after = (v < cur_v) || (v == cur_v && i > cur_i);
+        if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      cur_v = bv; cur_i = bi;
+    }
+    const float tau = cur_v - 2.f * eps;
+    // (d) candidate set
+    int nc = 0;
+    for (int i0 = 0; i0 < S; i0 += 32) {
+      int i = i0 + lane;
+      bool c = i < S && __half2float(ssc[i]) >= tau;
+      unsigned int m = __ballot_sync(0xffffffffu, c);
+      if (c) { int pos = nc + __popc(m & ((1u << lane) - 1u)); if (pos < RR_CAND) cidx[pos] = i; }
+      nc += __popc(m);
+    }
+    if (nc > RR_CAND) {   // pathological ties / huge norms: hand the query to the exact SIMT kernel
+      if (lane == 0) overflow[q] = 1;
+      continue;
+    }
+    __syncwarp();
+    // (e) exact fp32 centred cosine of every candidate
+    const float inv_n = 1.0f / (norm_qc > 1e-8f ? norm_qc : 1e-8f);
+    for (int j = 0; j < nc; j++) {
+      const float* brow = bhat + (size_t)cidx[j] * D;
+      float dot = 0.f;
+      for (int k = lane * 4; k < D; k += 128) {
+        float4 a = *reinterpret_cast<const float4*>(qc + k);
+        float4 b = __ldg(reinterpret_cast<const float4*>(brow + k));
+        dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+      for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (lane == 0) csim[j] = dot * inv_n;
+    }
+    __syncwarp();
+    // (f) exact top-k among the candidates (sim desc, index asc), votes, mode, keep
+    float pv = INFINITY; int pi = -1;
+    int64_t myvote = -1;   // lane r keeps the vote of rank r
+    for (int round = 0; round < topk; round++) {
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int j = lane; j < nc; j += 32) {
+        float v = csim[j]; int i = cidx[j];
+        bool after = (v < pv) || (v == pv && i > pi);
+        if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      pv = bv; pi = bi;
+      const int64_t vote = (bi != 0x7fffffff) ? bank_cls[bi] : -1;
+      if (lane == round) myvote = vote;
+      if (lane == 0) {
+        top_idx[q * topk + round] = (bi != 0x7fffffff) ? bi : -1;
+        votes[q * topk + round] = vote;
+        if (top_sim) top_sim[q * topk + round] = bv;
+      }
+    }
+    // torch.mode over the first knn votes: most frequent, smallest value on ties
+    const int kk = knn < topk ? knn : topk;
+    int cnt = 0;
+    for (int r2 = 0; r2 < kk; r2++) { int64_t v = __shfl_sync(0xffffffffu, myvote, r2); cnt += (lane < kk && v == myvote); }
+    int bc = (lane < kk) ? cnt : -1; int64_t bvv = myvote;
+    for (int o = 16; o; o >>= 1) {
+      int oc = __shfl_xor_sync(0xffffffffu, bc, o); int64_t ov = __shfl_xor_sync(0xffffffffu, bvv, o);
+      if (oc > bc || (oc == bc && ov < bvv)) { bc = oc; bvv = ov; }
+    }
+    if (lane == 0) keep[q] = (query_cls[q] == bvv) ? 1 : 0;
+  }
+}
+
 }  // namespace lvcb200
 
 using namespace lvcb200;
 
-extern "C" size_t lvcb200_knn_prepared_bytes(int S, int D) { return sizeof(float) * ((size_t)D + (size_t)S * D); }
+static inline int knn_s_pad(int S) { return (S + 7) / 8 * 8; }
+static inline int knn_s_al(int S) { return (S + 63) / 64 * 64; }
+// prepared layout: mean[D] | negc[S_al] | bhat[S_pad][D]
+extern "C" size_t lvcb200_knn_prepared_bytes(int S, int D) {
+  return sizeof(float) * ((size_t)D + knn_s_al(S) + (size_t)knn_s_pad(S) * D);
+}
 
 extern "C" int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_prepared, void* stream) {
   LVC_REQUIRE(S >= 1 && D >= 4 && D % 4 == 0, "knn_prepare: need S >= 1 and D a positive multiple of 4");
   LVC_REQUIRE(bank && bank_prepared, "knn_prepare: NULL pointer");
   cudaStream_t s = (cudaStream_t)stream;
   float* mean = (float*)bank_prepared;
-  float* bhat = mean + D;
+  float* negc = mean + D;
+  float* bhat = negc + knn_s_al(S);
   knn_mean_kernel<<<(D + 255) / 256, 256, 0, s>>>(bank, S, D, mean);
   int rc = check_launch("knn_mean_kernel");
   if (rc) return rc;
-  knn_normalize_kernel<<<S, 256, 0, s>>>(bank, D, mean, bhat);
+  knn_normalize_kernel<<<knn_s_pad(S), 256, 0, s>>>(bank, S, D, mean, bhat, negc);
   return check_launch("knn_normalize_kernel");
 }
 
@@ -171,6 +326,57 @@ extern "C" int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank
   LVC_REQUIRE(((uintptr_t)queries % 16) == 0, "knn_verify: queries must be 16-byte aligned");
   const float* mean = (const float*)bank_prepared;
   knn_verify_kernel<<<(unsigned)ceil_div64(Q, QT), 256, 0, (cudaStream_t)stream>>>(
-      mean, mean + D, bank_cls, S, D, queries, query_cls, Q, topk, knn, top_idx, top_sim, votes, keep);
+      mean, mean + D + knn_s_al(S), bank_cls, S, D, queries, query_cls, Q, topk, knn, top_idx, top_sim, votes, keep, nullptr);
+  return check_launch("knn_verify_kernel");
+}
+
+extern "C" size_t lvcb200_knn_tc_workspace(int64_t Q, int S) {
+  return align_up((size_t)Q * knn_s_pad(S) * 2, 256) + align_up((size_t)Q, 256);
+}
+
+extern "C" int lvcb200_knn_verify_tc(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
+                                     const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
+                                     int64_t* votes, uint8_t* keep, void* workspace, size_t workspace_bytes, void* stream) {
+  LVC_REQUIRE(S >= 64 && S <= 4096 && D >= 32 && D % 8 == 0 && D <= 4096, "knn_verify_tc: need 64 <= S <= 4096, D a multiple of 8 in [32, 4096]");
+  LVC_REQUIRE(topk >= 1 && topk <= KNN_MAXK && topk <= S && knn >= 1, "knn_verify_tc: need 1 <= topk <= min(16, S), knn >= 1");
+  if (Q == 0) return 0;
+  LVC_REQUIRE(bank_prepared && bank_cls && queries && query_cls && top_idx && votes && keep && workspace, "knn_verify_tc: NULL pointer");
+  LVC_REQUIRE(((uintptr_t)queries % 16) == 0, "knn_verify_tc: queries must be 16-byte aligned");
+  if (workspace_bytes < lvcb200_knn_tc_workspace(Q, S)) return set_error(LVCB200_EWORKSPACE, "knn_verify_tc: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S_pad = knn_s_pad(S);
+  const float* mean = (const float*)bank_prepared;
+  const float* negc = mean + D;
+  const float* bhat = negc + knn_s_al(S);
+  __half* scores = (__half*)workspace;
+  uint8_t* overflow = (uint8_t*)workspace + align_up((size_t)Q * S_pad * 2, 256);
+  LVC_CUDA(cudaMemsetAsync(overflow, 0, (size_t)Q, st));
+  // (1) approximate scores on the tensor cores: scores[q, s] = q . bhat_s - mu . bhat_s   (TF32 operands, fp16 out)
+  lvcb200_gemm_desc g;
+  memset(&g, 0, sizeof(g));
+  g.a_dtype = LVCB200_F32;
+  g.A = queries; g.lda = D; g.M_rows = Q;
+  g.W = bhat; g.ldw = D;
+  g.bias = negc;
+  g.D = scores; g.ldd = S_pad; g.d_dtype = LVCB200_F16;
+  g.M = Q; g.N = S_pad; g.K = D; g.taps = 1;
+  int rc = lvcb200_gemm_bf16(&g, stream);
+  if (rc) return rc;
+  // (2) rigorous candidate selection + exact fp32 re-scoring
+  const size_t per_warp = (((size_t)S_pad * 2 + 15) / 16 * 16 + (size_t)D * 4 + RR_CAND * 8 + 15) / 16 * 16;
+  const size_t smem = per_warp * RR_WARPS;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    LVC_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  int64_t blocks = ceil_div64(Q, RR_WARPS);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  knn_rerank_kernel<<<(unsigned)blocks, RR_WARPS * 32, smem, st>>>(mean, bhat, bank_cls, S, S_pad, D, queries, query_cls, Q, scores, topk,
+                                                                 knn, top_idx, top_sim, votes, keep, overflow);
+  if ((rc = check_launch("knn_rerank_kernel"))) return rc;
+  // (3) exact SIMT pass over the (normally zero) queries whose candidate set overflowed
+  knn_verify_kernel<<<(unsigned)ceil_div64(Q, QT), 256, 0, st>>>(mean, bhat, bank_cls, S, D, queries, query_cls, Q, topk, knn, top_idx,
+                                                                top_sim, votes, keep, overflow);
   return check_launch("knn_verify_kernel");
 }

@@ -165,28 +165,30 @@ constexpr int kMaxSepGrid = 16;
 // Bilinear weights are separable (w(y,x) = wy(y) * wx(x)) and the sample grid of a bin is a product grid, so
 //   sum_{iy,ix} sum_{corners} w * f  ==  sum_{rows} sum_{cols} Wy[row] * Wx[col] * f[row, col]
 // with Wy / Wx the per-row / per-column sums of the 1-D weights.  A bin with a g x g sample grid then reads (g+1)^2
-// pixel vectors instead of 4 g^2 -- the gather is L2-bandwidth bound, so this is the whole cost.
+// pixel vectors instead of 4 g^2.  One warp owns one (RoI, bin-row): the RoI geometry, the level assignment, Wy and the
+// seven Wx tables are computed once and reused for the seven bins of the row (the first version recomputed them per bin and
+// was instruction-issue bound at 2 100 instructions per bin, see profiles/).
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t R, int P, int sampling_ratio,
                     int canon_size, int canon_level, int min_level, TO* __restrict__ out, int out_layout,
                     int64_t out_pitch, int64_t* __restrict__ levels_out) {
   constexpr int V = Vec<TI>::N;
-  __shared__ float sWy[8][kMaxSepGrid + 4], sWx[8][kMaxSepGrid + 4];
+  constexpr int MAXP = 8, WS = kMaxSepGrid + 4;
+  __shared__ float sWy[8][WS], sWx[8][MAXP][WS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int bins = P * P;
-  for (int64_t item = warp; item < R * bins; item += nwarps) {
-    int64_t r = item / bins;
-    int bin = (int)(item - r * bins);
-    int ph = bin / P, pw = bin - ph * P;
+  for (int64_t item = warp; item < R * P; item += nwarps) {
+    const int64_t r = item / P;
+    const int ph = (int)(item - r * P);
     const float* roi = rois + r * 5;
     float rx1 = roi[1], ry1 = roi[2], rx2 = roi[3], ry2 = roi[4];
     int lvl = 0;
     if (L.n_levels > 1)
       lvl = assign_level(rx1, ry1, rx2, ry2, min_level, min_level + L.n_levels - 1, canon_size, canon_level);
-    if (levels_out != nullptr && bin == 0 && lane == 0) levels_out[r] = lvl;
+    if (levels_out != nullptr && ph == 0 && lane == 0) levels_out[r] = lvl;
     const bool no_level = lvl < 0;  // reference: `level_assignments == level` never true -> row stays zero
     if (no_level) lvl = 0;
     const lvcb200_fmap fm = L.lv[lvl];
@@ -194,79 +196,79 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
     RoiGeom g = roi_geom(roi, fm.spatial_scale, P, P, sampling_ratio, true);
     const int gh = no_level ? 0 : g.grid_h, gw = no_level ? 0 : g.grid_w;
     const TI* base = reinterpret_cast<const TI*>(fm.base) + (int64_t)roi[0] * fm.img_stride * fm.c_stride;
-    const bool separable = gh >= 1 && gw >= 1 && gh <= kMaxSepGrid && gw <= kMaxSepGrid;
-    int ybase = 0, ny = 0, xbase = 0, nx = 0;
+    const bool separable = gh >= 1 && gw >= 1 && gh <= kMaxSepGrid && gw <= kMaxSepGrid && P <= MAXP;
+    const float inv_count = 1.0f / g.count;
+    int ybase = 0, ny = 0;
+    const float ystep = gh > 0 ? g.bin_h / (float)gh : 0.f, xstep = gw > 0 ? g.bin_w / (float)gw : 0.f;
+    const float y_first = g.start_h + ph * g.bin_h;
     if (separable) {
-      const float y_first = g.start_h + ph * g.bin_h, x_first = g.start_w + pw * g.bin_w;
-      ybase = make_tap1(y_first + .5f * g.bin_h / (float)gh, H).lo;
-      ny = make_tap1(y_first + ((float)(gh - 1) + .5f) * g.bin_h / (float)gh, H).hi - ybase + 1;
-      xbase = make_tap1(x_first + .5f * g.bin_w / (float)gw, W).lo;
-      nx = make_tap1(x_first + ((float)(gw - 1) + .5f) * g.bin_w / (float)gw, W).hi - xbase + 1;
       __syncwarp();
-      if (lane < ny) {
-        float wsum = 0.f;
-        for (int i = 0; i < gh; i++) {
-          Tap1 t = make_tap1(y_first + ((float)i + .5f) * g.bin_h / (float)gh, H);
-          if (!t.valid) continue;
-          if (t.lo == ybase + lane) wsum += t.wlo;
-          if (t.hi == ybase + lane) wsum += t.whi;
-        }
-        sWy[wib][lane] = wsum;
+      for (int i = lane; i < WS; i += 32) sWy[wib][i] = 0.f;
+      for (int i = lane; i < MAXP * WS; i += 32) (&sWx[wib][0][0])[i] = 0.f;
+      ybase = make_tap1(y_first + .5f * ystep, H).lo;
+      ny = make_tap1(y_first + ((float)(gh - 1) + .5f) * ystep, H).hi - ybase + 1;
+      __syncwarp();
+      if (lane < gh) {
+        Tap1 t = make_tap1(y_first + ((float)lane + .5f) * ystep, H);
+        if (t.valid) { atomicAdd(&sWy[wib][t.lo - ybase], t.wlo); atomicAdd(&sWy[wib][t.hi - ybase], t.whi); }
       }
-      if (lane < nx) {
-        float wsum = 0.f;
-        for (int i = 0; i < gw; i++) {
-          Tap1 t = make_tap1(x_first + ((float)i + .5f) * g.bin_w / (float)gw, W);
-          if (!t.valid) continue;
-          if (t.lo == xbase + lane) wsum += t.wlo;
-          if (t.hi == xbase + lane) wsum += t.whi;
-        }
-        sWx[wib][lane] = wsum;
+      for (int sidx = lane; sidx < P * gw; sidx += 32) {
+        const int pw = sidx / gw, i = sidx - pw * gw;
+        const float x_first = g.start_w + pw * g.bin_w;
+        const int xb = make_tap1(x_first + .5f * xstep, W).lo;
+        Tap1 t = make_tap1(x_first + ((float)i + .5f) * xstep, W);
+        if (t.valid) { atomicAdd(&sWx[wib][pw][t.lo - xb], t.wlo); atomicAdd(&sWx[wib][pw][t.hi - xb], t.whi); }
       }
       __syncwarp();
     }
     for (int c0 = lane * V; c0 < C; c0 += 32 * V) {
-      float acc[V];
+      for (int pw = 0; pw < P; pw++) {
+        const int bin = ph * P + pw;
+        float acc[V];
 #pragma unroll
-      for (int i = 0; i < V; i++) acc[i] = 0.f;
-      if (separable) {
-        for (int ry = 0; ry < ny; ry++) {
-          const float wy = sWy[wib][ry];
-          if (wy == 0.f) continue;
-          const TI* rowp = base + ((int64_t)(ybase + ry) * fm.row_stride + xbase) * fm.c_stride + c0;
-          for (int rx = 0; rx < nx; rx++) {
-            const float w = wy * sWx[wib][rx];
-            if (w == 0.f) continue;
-            float v[V];
-            Vec<TI>::load(rowp + (int64_t)rx * fm.c_stride, v);
+        for (int i = 0; i < V; i++) acc[i] = 0.f;
+        if (separable) {
+          const float x_first = g.start_w + pw * g.bin_w;
+          const int xbase = make_tap1(x_first + .5f * xstep, W).lo;
+          const int nx = make_tap1(x_first + ((float)(gw - 1) + .5f) * xstep, W).hi - xbase + 1;
+          for (int ry = 0; ry < ny; ry++) {
+            const float wy = sWy[wib][ry];
+            if (wy == 0.f) continue;
+            const TI* rowp = base + ((int64_t)(ybase + ry) * fm.row_stride + xbase) * fm.c_stride + c0;
+#pragma unroll 2
+            for (int rx = 0; rx < nx; rx++) {
+              const float w = wy * sWx[wib][pw][rx];
+              float v[V];
+              Vec<TI>::load(rowp + (int64_t)rx * fm.c_stride, v);
 #pragma unroll
-            for (int i = 0; i < V; i++) acc[i] += w * v[i];
+              for (int i = 0; i < V; i++) acc[i] += w * v[i];
+            }
+          }
+        } else {
+          for (int iy = 0; iy < gh; iy++) {
+            float y = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
+            for (int ix = 0; ix < gw; ix++) {
+              float x = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
+              Tap t = make_tap(y, x, H, W);
+              if (!t.valid) continue;
+              float v1[V], v2[V], v3[V], v4[V];
+              Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x0) * fm.c_stride + c0, v1);
+              Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x1) * fm.c_stride + c0, v2);
+              Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x0) * fm.c_stride + c0, v3);
+              Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x1) * fm.c_stride + c0, v4);
+#pragma unroll
+              for (int i = 0; i < V; i++) acc[i] += t.w1 * v1[i] + t.w2 * v2[i] + t.w3 * v3[i] + t.w4 * v4[i];
+            }
           }
         }
-      } else {
-        for (int iy = 0; iy < gh; iy++) {
-          float y = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
-          for (int ix = 0; ix < gw; ix++) {
-            float x = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
-            Tap t = make_tap(y, x, H, W);
-            if (!t.valid) continue;
-            float v1[V], v2[V], v3[V], v4[V];
-            Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x0) * fm.c_stride + c0, v1);
-            Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x1) * fm.c_stride + c0, v2);
-            Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x0) * fm.c_stride + c0, v3);
-            Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x1) * fm.c_stride + c0, v4);
 #pragma unroll
-            for (int i = 0; i < V; i++) acc[i] += t.w1 * v1[i] + t.w2 * v2[i] + t.w3 * v3[i] + t.w4 * v4[i];
-          }
+        for (int i = 0; i < V; i++) acc[i] = acc[i] * inv_count;
+        if (out_layout == LVCB200_OUT_NHWC) {
+          store_vec<TO, V>(out + r * out_pitch + (int64_t)bin * C + c0, acc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; i++) out[r * out_pitch + (int64_t)(c0 + i) * bins + bin] = (TO)acc[i];
         }
-      }
-#pragma unroll
-      for (int i = 0; i < V; i++) acc[i] = acc[i] / g.count;
-      if (out_layout == LVCB200_OUT_NHWC) {
-        store_vec<TO, V>(out + r * out_pitch + (int64_t)bin * C + c0, acc);
-      } else {
-#pragma unroll
-        for (int i = 0; i < V; i++) out[r * out_pitch + (int64_t)(c0 + i) * bins + bin] = (TO)acc[i];
       }
     }
     __syncwarp();
@@ -317,7 +319,7 @@ extern "C" int lvcb200_roi_pool_fpn(const lvcb200_fmap* levels, int n_levels, in
     LVC_REQUIRE(((uintptr_t)levels[i].base % 16) == 0 && levels[i].c_stride % V == 0, "roi_pool_fpn: level not 16B aligned");
   }
   int threads = 256;
-  int64_t warps = R * pooled * pooled;
+  int64_t warps = R * pooled;   // one warp per (RoI, bin row)
   int64_t blocks = ceil_div64(warps, threads / 32);
   if (blocks > (int64_t)kNumSMs * 256) blocks = (int64_t)kNumSMs * 256;
   cudaStream_t s = (cudaStream_t)stream;

@@ -31,6 +31,8 @@ def _workspace(tag, nbytes, device):
 
 
 def _dt(t):
+    if t.dtype == torch.float16:
+        return _lib.F16
     if t.dtype == torch.bfloat16:
         return BF16
     if t.dtype == torch.float32:
@@ -219,7 +221,11 @@ class KnnBank:
         rc = lib.lvcb200_knn_prepare(_lib.ptr(self.bank), self.S, self.D, _lib.ptr(self.prepared), _lib.stream_ptr())
         _lib.check(rc, "lvcb200_knn_prepare")
 
-    def verify(self, queries, query_cls, topk=10, knn=10, return_sim=False):
+    def tc_eligible(self):
+        return 64 <= self.S <= 4096 and self.D % 8 == 0 and 32 <= self.D <= 4096
+
+    def verify(self, queries, query_cls, topk=10, knn=10, return_sim=False, path="auto"):
+        """path: "auto" (tensor-core scores + exact re-rank when the bank shape allows it), "tc", or "simt" (exact fp32 FMA)."""
         _lib.require_cuda(queries, query_cls)
         q = queries.detach().to(torch.float32).contiguous()
         qc = query_cls.detach().to(torch.int64).contiguous()
@@ -229,10 +235,18 @@ class KnnBank:
         votes = torch.empty((Q, topk), dtype=torch.int64, device=dev)
         keep = torch.empty(Q, dtype=torch.uint8, device=dev)
         sim = torch.empty((Q, topk), dtype=torch.float32, device=dev) if return_sim else None
-        rc = _lib.load().lvcb200_knn_verify(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
-                                            topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep),
-                                            _lib.stream_ptr())
-        _lib.check(rc, "lvcb200_knn_verify")
+        lib = _lib.load()
+        use_tc = path == "tc" or (path == "auto" and self.tc_eligible() and Q > 0)
+        if use_tc:
+            ws = _workspace("knn", lib.lvcb200_knn_tc_workspace(Q, self.S), dev)
+            rc = lib.lvcb200_knn_verify_tc(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
+                                           topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep), _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "lvcb200_knn_verify_tc")
+        else:
+            rc = lib.lvcb200_knn_verify(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
+                                        topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep), _lib.stream_ptr())
+            _lib.check(rc, "lvcb200_knn_verify")
         return dict(top_idx=top_idx, votes=votes, keep=keep, top_sim=sim)
 
 
@@ -242,7 +256,7 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
     """D = act(sum_t A[m+shift_t, :K] @ W[:, t*K:(t+1)*K]^T + bias + residual).  A [rows, >=K] bf16 (row pitch = stride(0)),
     W [N, taps*K] bf16.  plane_hw=(PH, PW) zeroes border rows of a zero-bordered plane."""
     _lib.require_cuda(A, W, bias, residual, out)
-    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and A.stride(1) == 1 and W.stride(1) == 1
+    assert A.dtype == W.dtype and A.dtype in (torch.bfloat16, torch.float32) and A.stride(1) == 1 and W.stride(1) == 1
     N = W.shape[0]
     K = K or (W.shape[1] // taps)
     M = M if M is not None else A.shape[0]
@@ -250,6 +264,7 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
         out = torch.empty((M, N), dtype=out_dtype, device=A.device)
     assert out.stride(1) == 1
     d = GemmDesc()
+    d.a_dtype = _dt(A)
     d.A, d.lda, d.M_rows = A.data_ptr(), A.stride(0), A.shape[0]
     d.W, d.ldw = W.data_ptr(), W.stride(0)
     d.bias = bias.data_ptr() if bias is not None else None

@@ -34,7 +34,7 @@ def test_abi_version_and_error_channel():
     rc = lib.lvcb200_gemm_bf16(None, None)
     assert rc == -1 and b"NULL" in lib.lvcb200_last_error()
     assert lib.lvcb200_batched_nms_workspace(1000) > 1000 * 20
-    assert lib.lvcb200_knn_prepared_bytes(600, 1024) == 4 * (1024 + 600 * 1024)
+    assert lib.lvcb200_knn_prepared_bytes(600, 1024) == 4 * (1024 + 640 + 600 * 1024)   # mean | -c_s (padded) | bhat
 
 
 def test_no_cpu_fallback():

@@ -96,3 +96,21 @@ def test_conv1x1_residual_block_tail():
     out = ops.gemm(px.t.view(-1, Cin), w.view(Cout, Cin), bias=bias, residual=ps.t.view(-1, Cout), relu=True, plane_hw=(H + 2, W + 2))
     want = torch.relu(F.conv2d(x.float(), w.float(), bias) + sc.float())
     _close(ops.Plane(out.view(n, H + 2, W + 2, Cout), H, W, Cout).to_nchw(), want, True)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 600, 1024), (4096, 256, 384), (130, 2400, 384)])
+def test_gemm_tf32_operands_f16_out(M, N, K):
+    """kNN score GEMM: fp32 operands consumed as TF32 (kind::tf32), fp16 output, bias = -c_s.  Checker: fp32 matmul of the
+    tf32-truncated... the tensor core may round or truncate to 10 mantissa bits, so the bound is the rigorous one used by the
+    re-rank stage: |err| <= 2^-9 * |a| * |w| per row/col pair (+ fp16 output rounding 2^-11 * |value|)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float16)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = a @ w.t() + bias
+    bound = 2.0 ** -9 * a.norm(dim=1, keepdim=True) * w.norm(dim=1)[None, :] + 2.0 ** -10 * ref.abs() + 1e-6
+    assert bool(((out.float() - ref).abs() <= bound).all()), float(((out.float() - ref).abs() / bound).max())
+    # and it is genuinely more accurate than bf16 operands would be (typical error ~ 2^-11 / sqrt(K) scale)
+    assert float((out.float() - ref).abs().mean()) < 2e-3 * float(ref.abs().mean())

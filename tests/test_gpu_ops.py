@@ -283,14 +283,21 @@ def test_knn_vs_oracle_tie_aware():
     qc = rng.integers(0, ncls, Q).astype(np.int64)
     q = rng.standard_normal((Q, D)).astype(np.float32) + means[qc] + 3.0
     want = O.knn_verify(bank, cls, q, qc)
-    got = ops.KnnBank(cu(bank), cu(cls)).verify(cu(q), cu(qc), return_sim=True)
-    gi, gs = got["top_idx"].cpu().numpy(), got["top_sim"].cpu().numpy()
-    np.testing.assert_allclose(gs, want["top_sim"], rtol=1e-3, atol=2e-6)
-    bad = gi != want["top_idx"]
-    assert bad.mean() < 1e-3
-    assert np.all(np.abs(gs[bad] - want["top_sim"][bad]) < 1e-5)      # only near-ties may swap
-    rows_bad = bad.any(1)
-    assert np.array_equal(got["keep"].cpu().numpy()[~rows_bad], want["keep"][~rows_bad])
+    kb = ops.KnnBank(cu(bank), cu(cls))
+    for path in ("simt", "tc"):     # exact fp32 FMA kernel; tensor-core (TF32 scores + rigorous candidates + exact re-rank)
+        got = kb.verify(cu(q), cu(qc), return_sim=True, path=path)
+        gi, gs = got["top_idx"].cpu().numpy(), got["top_sim"].cpu().numpy()
+        np.testing.assert_allclose(gs, want["top_sim"], rtol=1e-3, atol=2e-6)
+        bad = gi != want["top_idx"]
+        assert bad.mean() < 1e-3, path
+        assert np.all(np.abs(gs[bad] - want["top_sim"][bad]) < 1e-5), path      # only near-ties may swap
+        rows_bad = bad.any(1)
+        assert np.array_equal(got["keep"].cpu().numpy()[~rows_bad], want["keep"][~rows_bad]), path
+    # candidate-set overflow (all bank rows identical -> every score ties) must fall back to the exact kernel, not fail
+    same = np.repeat(bank[:1], 128, 0) + np.arange(128, dtype=np.float32)[:, None] * 0     # 128 identical rows
+    r_tc = ops.KnnBank(cu(same), cu(cls[:128])).verify(cu(q[:64]), cu(qc[:64]), path="tc")
+    r_si = ops.KnnBank(cu(same), cu(cls[:128])).verify(cu(q[:64]), cu(qc[:64]), path="simt")
+    assert torch.equal(r_tc["keep"], r_si["keep"]) and torch.equal(r_tc["votes"], r_si["votes"])
     # ragged / tiny inputs
     r1 = ops.KnnBank(cu(bank[:37]), cu(cls[:37])).verify(cu(q[:5]), cu(qc[:5]), topk=10, knn=5)
     w1 = O.knn_verify(bank[:37], cls[:37], q[:5], qc[:5], topk=10, knn=5)
