@@ -125,6 +125,95 @@ def cpu_baseline(cfg, sd, n_images=2):
             "sample": f"{n_images} images of the same 3x800x1333 R101-FPN workload, batch 1 as in the reference's test loader"}
 
 
+def knn_section(rank, world, dev, dist, with_cpu):
+    """BASELINE config #4: label-verification kNN, 200k x 1024 queries vs a 20-class x 30-shot bank, cosine top-10; the bank is
+    row-sharded over ranks and assembled with ONE all-gather; queries are sharded (strong scaling over the fixed 200k)."""
+    from lvc_b200 import ops
+    from lvc_b200.knn import all_gather_bank
+    S, D, Q, ncls = 600, 1024, 200_000, 20
+    g = torch.Generator(device=dev).manual_seed(1)
+    means = torch.zeros(ncls, D, device=dev)
+    means[torch.arange(ncls), torch.arange(ncls)] = 0.5 * 8        # class-dependent shift so that votes are non-trivial
+    cls_all = torch.arange(ncls, device=dev).repeat_interleave(S // ncls)
+    bank_all = torch.randn(S, D, generator=g, device=dev) + means[cls_all]
+    lo, hi = rank * S // world, (rank + 1) * S // world
+    ql, qh = rank * Q // world, (rank + 1) * Q // world
+    g2 = torch.Generator(device=dev).manual_seed(2 + rank)
+    qcls = torch.randint(0, ncls, (qh - ql,), generator=g2, device=dev)
+    queries = torch.randn(qh - ql, D, generator=g2, device=dev) + means[qcls]
+    res = {}
+    for path in ("tc", "simt"):
+        times = []
+        for it in range(4):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c, b = all_gather_bank(cls_all[lo:hi], bank_all[lo:hi])          # the one exchange step
+            kb = ops.KnnBank(b, c)
+            out = kb.verify(queries, qcls, topk=10, knn=10, path=path)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(times[1:])], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        alg_bytes = Q * D * 4 + S * D * 4 + Q * 10 * 8 + Q            # SURVEY 8(d): 837.9 MB
+        res[path] = {"ms": ms, "queries_per_s": Q / (ms / 1e3), "hbm_gbs": alg_bytes / (ms / 1e3) / 1e9}
+        if path == "tc":
+            res["keep_fraction_rank0"] = float(out["keep"].float().mean())
+        if path == "simt" and world > 1:
+            pass
+    peak_tf, peak_hbm, which = measured_peaks()
+    out = {"workload": "200k x 1024 fp32 queries vs 600 x 1024 bank (20 classes x 30 shots), centred cosine top-10 + mode vote",
+           "tensor_core_path": res["tc"], "simt_exact_path": res["simt"],
+           "roofline": {"bound": "hbm", "achieved": res["tc"]["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s",
+                        "frac": res["tc"]["hbm_gbs"] / peak_hbm / world, "algorithmic_bytes": 837.9e6,
+                        "note": "includes the bank all-gather + bank preparation inside the timed region"},
+           "keep_fraction_rank0": res.get("keep_fraction_rank0")}
+    if with_cpu and rank == 0:
+        from oracle import oracle as O
+        torch.set_num_threads(os.cpu_count())
+        qs, bs, cs = queries[:20000].cpu().numpy(), bank_all.cpu().numpy(), cls_all.cpu().numpy()
+        t0 = time.time()
+        O.knn_reference_form_torch(bs, cs, qs[:2000], per_call=5)
+        t_ref = (time.time() - t0) / 2000
+        t0 = time.time()
+        O.knn_verify_batched_torch(bs, cs, qs, qcls[:20000].cpu().numpy())
+        t_b = (time.time() - t0) / 20000
+        out["cpu_baseline"] = {"reference_form_queries_per_s": 1.0 / t_ref, "batched_gemm_form_queries_per_s": 1.0 / t_b,
+                               "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "2000 queries in the reference's per-image broadcast form (5 per call); 20000 in batched form"}
+    return out
+
+
+def corrector_section(dev):
+    """BASELINE config #5: box-corrector regression head (fc 12544->1024->1024->1024->4) over 100k pooled 7x7x256 RoIs, bf16."""
+    from lvc_b200.config import DetectorConfig
+    from lvc_b200.modeling import BoxCorrectorHead
+    from lvc_b200.weights import synthetic_corrector_head
+    cfg = DetectorConfig(depth=50, num_fc=3)
+    head = BoxCorrectorHead(cfg, synthetic_corrector_head(cfg, 3), dev)
+    R = 100_000
+    pooled = torch.randn(R, 12544, device=dev, dtype=torch.bfloat16, generator=torch.Generator(device=dev).manual_seed(3))
+    for _ in range(2):
+        head.head(0, pooled)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        head.head(0, pooled)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    flop = 2.0 * R * (12544 * 1024 + 1024 * 1024 * 2 + 1024 * 4)
+    peak_tf, _, which = measured_peaks()
+    return {"workload": "one corrector stage head over 100k pooled RoIs [100000, 12544] bf16", "ms": ms, "rois_per_s": R / (ms / 1e3),
+            "tflops": flop / (ms / 1e3) / 1e12, "frac_of_peak": flop / (ms / 1e3) / 1e12 / peak_tf}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Python and cannot travel to
     the GPU box (no /root/reference there), so this times the oracle port (oracle/model.py) on all host threads."""
@@ -164,6 +253,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--gemm-table", default=None, help="write per-GEMM-launch timings of the roofline pass to this file")
+    ap.add_argument("--no-extras", action="store_true", help="skip the kNN (config #4) and box-corrector (config #5) sections")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -284,6 +374,12 @@ def main():
                 "avg_launch_ms": gemm_ms / max(n_gemm, 1), "gemm_ms_per_step": gemm_ms, "algorithmic_tflop_per_step": alg_tflop,
                 "gemm_share_of_step": gemm_ms / (ms / K)}
 
+    extras = {}
+    if not args.no_extras:
+        extras["knn"] = knn_section(rank, world, dev, dist, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        if rank == 0 and world == 1:
+            extras["box_corrector"] = corrector_section(dev)
+
     if rank == 0:
         imgs = world * BATCH * K
         line = {"metric": METRIC, "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
@@ -300,6 +396,7 @@ def main():
                         "api": "lvc_b200.modeling.GeneralizedRCNN(batched_inputs) with pinned host fp32 images"},
                 "gpu_launches": launches_per_step * K,
                 "roofline": roof}
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, sd)
         print(json.dumps(line))

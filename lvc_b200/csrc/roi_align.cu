@@ -111,6 +111,13 @@ struct PoolLevels {
 template <typename T> struct Vec;
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
+  __device__ static uint4 load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static void unpack(const uint4& u, float* v) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+    v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
   __device__ static void load(const __nv_bfloat16* p, float* v) {
     uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -120,6 +127,10 @@ template <> struct Vec<__nv_bfloat16> {
 };
 template <> struct Vec<float> {
   static constexpr int N = 4;
+  __device__ static uint4 load_raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static void unpack(const uint4& u, float* v) {
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+  }
   __device__ static void load(const float* p, float* v) {
     float4 u = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
@@ -160,7 +171,7 @@ __device__ __forceinline__ Tap1 make_tap1(float y, int size) {
   return t;
 }
 
-constexpr int kMaxSepGrid = 16;
+constexpr int kMaxSepGrid = 32;
 
 // Bilinear weights are separable (w(y,x) = wy(y) * wx(x)) and the sample grid of a bin is a product grid, so
 //   sum_{iy,ix} sum_{corners} w * f  ==  sum_{rows} sum_{cols} Wy[row] * Wx[col] * f[row, col]
@@ -168,8 +179,30 @@ constexpr int kMaxSepGrid = 16;
 // pixel vectors instead of 4 g^2.  One warp owns one (RoI, bin-row): the RoI geometry, the level assignment, Wy and the
 // seven Wx tables are computed once and reused for the seven bins of the row (the first version recomputed them per bin and
 // was instruction-issue bound at 2 100 instructions per bin, see profiles/).
+// Slow generic path for sample grids larger than the separable tables (RoIs wider than 224 feature pixels at their level).
+template <typename TI, int V>
+__device__ __noinline__ void roi_bin_generic(const TI* base, const lvcb200_fmap& fm, const RoiGeom& g, int gh, int gw, int ph, int pw,
+                                             int c0, float* acc) {
+  const int H = fm.H, W = fm.W;
+  for (int iy = 0; iy < gh; iy++) {
+    float y = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
+    for (int ix = 0; ix < gw; ix++) {
+      float x = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
+      Tap t = make_tap(y, x, H, W);
+      if (!t.valid) continue;
+      float v1[V], v2[V], v3[V], v4[V];
+      Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x0) * fm.c_stride + c0, v1);
+      Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x1) * fm.c_stride + c0, v2);
+      Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x0) * fm.c_stride + c0, v3);
+      Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x1) * fm.c_stride + c0, v4);
+#pragma unroll
+      for (int i = 0; i < V; i++) acc[i] += t.w1 * v1[i] + t.w2 * v2[i] + t.w3 * v3[i] + t.w4 * v4[i];
+    }
+  }
+}
+
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t R, int P, int sampling_ratio,
                     int canon_size, int canon_level, int min_level, TO* __restrict__ out, int out_layout,
                     int64_t out_pitch, int64_t* __restrict__ levels_out) {
@@ -235,31 +268,25 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
             const float wy = sWy[wib][ry];
             if (wy == 0.f) continue;
             const TI* rowp = base + ((int64_t)(ybase + ry) * fm.row_stride + xbase) * fm.c_stride + c0;
-#pragma unroll 2
-            for (int rx = 0; rx < nx; rx++) {
-              const float w = wy * sWx[wib][pw][rx];
-              float v[V];
-              Vec<TI>::load(rowp + (int64_t)rx * fm.c_stride, v);
+            for (int rx0 = 0; rx0 < nx; rx0 += 8) {        // 8 independent 16-byte loads in flight per lane
+              uint4 raw[8];
 #pragma unroll
-              for (int i = 0; i < V; i++) acc[i] += w * v[i];
+              for (int u = 0; u < 8; u++) {
+                const int rx = (rx0 + u < nx) ? rx0 + u : nx - 1;   // clamp: a duplicate load, weight forced to 0 below
+                raw[u] = Vec<TI>::load_raw(rowp + (int64_t)rx * fm.c_stride);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const float w = (rx0 + u < nx) ? wy * sWx[wib][pw][rx0 + u] : 0.f;
+                float v[V];
+                Vec<TI>::unpack(raw[u], v);
+#pragma unroll
+                for (int i = 0; i < V; i++) acc[i] += w * v[i];
+              }
             }
           }
         } else {
-          for (int iy = 0; iy < gh; iy++) {
-            float y = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
-            for (int ix = 0; ix < gw; ix++) {
-              float x = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
-              Tap t = make_tap(y, x, H, W);
-              if (!t.valid) continue;
-              float v1[V], v2[V], v3[V], v4[V];
-              Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x0) * fm.c_stride + c0, v1);
-              Vec<TI>::load(base + ((int64_t)t.y0 * fm.row_stride + t.x1) * fm.c_stride + c0, v2);
-              Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x0) * fm.c_stride + c0, v3);
-              Vec<TI>::load(base + ((int64_t)t.y1 * fm.row_stride + t.x1) * fm.c_stride + c0, v4);
-#pragma unroll
-              for (int i = 0; i < V; i++) acc[i] += t.w1 * v1[i] + t.w2 * v2[i] + t.w3 * v3[i] + t.w4 * v4[i];
-            }
-          }
+          roi_bin_generic<TI, V>(base, fm, g, gh, gw, ph, pw, c0, acc);
         }
 #pragma unroll
         for (int i = 0; i < V; i++) acc[i] = acc[i] * inv_count;
