@@ -270,6 +270,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(bar_tempty + 8 * b, bph ^ 1u);   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + b * BLOCK_N;
+        // a partial last N tile issues a narrower MMA (N rounded up to 16): no tensor-pipe time for padding columns
+        const int n_rem = p.N - n0;
+        const int n_eff = n_rem >= BLOCK_N ? BLOCK_N : ((n_rem + 15) & ~15);
+        const uint32_t idesc_t = (idesc & ~(0x3fu << 17)) | ((uint32_t)(n_eff >> 3) << 17);
         for (int ki = 0; ki < k_iters; ki++, it++) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait(bar_full + 8 * s, ph);
@@ -278,8 +282,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint64_t bdesc = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++) {  // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
-            if constexpr (KIND == 1) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            if constexpr (KIND == 1) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(bar_empty + 8 * s);             // frees the smem slot once these MMAs have read it
         }
@@ -505,7 +509,7 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   LVC_REQUIRE(d->M < (1ll << 31) && d->M_rows < (1ll << 31), "gemm: M too large");
   int bn = d->N >= 256 ? 256 : (d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16)));
   if (d->N > 128 && d->N < 256) bn = 256;
-  if (tf32) bn = ((d->N + 127) / 128 * 128 < (d->N + 255) / 256 * 256) ? 128 : 256;   // less column padding wins
+  if (tf32) bn = d->N > 128 ? 256 : 128;   // fp32 operands double the smem bytes per MMA: wide tiles keep B traffic per flop low
   // epilogue mode: fp32 output -> direct stores from registers; bf16 output -> smem staging + TMA stores
   const int mode = d->d_dtype == LVCB200_F32 ? 0 : 1;
   if ((mode == 1 || d->residual) && bn < 64) bn = 64;

@@ -243,16 +243,23 @@ knn_rerank_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
     __syncwarp();
     // (e) exact fp32 centred cosine of every candidate
     const float inv_n = 1.0f / (norm_qc > 1e-8f ? norm_qc : 1e-8f);
-    for (int j = 0; j < nc; j++) {
-      const float* brow = bhat + (size_t)cidx[j] * D;
-      float dot = 0.f;
+    for (int j0 = 0; j0 < nc; j0 += 4) {   // four candidates per pass: 4x the loads in flight per lane
+      const float* br[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) br[u] = bhat + (size_t)cidx[(j0 + u < nc) ? j0 + u : j0] * D;
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = lane * 4; k < D; k += 128) {
-        float4 a = *reinterpret_cast<const float4*>(qc + k);
-        float4 b = __ldg(reinterpret_cast<const float4*>(brow + k));
-        dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        const float4 a = *reinterpret_cast<const float4*>(qc + k);
+        float4 b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) b[u] = __ldg(reinterpret_cast<const float4*>(br[u] + k));
+#pragma unroll
+        for (int u = 0; u < 4; u++) dot[u] += a.x * b[u].x + a.y * b[u].y + a.z * b[u].z + a.w * b[u].w;
       }
-      for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      if (lane == 0) csim[j] = dot * inv_n;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        for (int o = 16; o; o >>= 1) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+      if (lane < 4 && j0 + lane < nc) csim[j0 + lane] = (lane == 0 ? dot[0] : lane == 1 ? dot[1] : lane == 2 ? dot[2] : dot[3]) * inv_n;
     }
     __syncwarp();
     // (f) exact top-k among the candidates (sim desc, index asc), votes, mode, keep
