@@ -282,7 +282,9 @@ def main():
     # rank r processes its own contiguous block of the synthetic image stream (InferenceSampler rule)
     seed0 = rank * BATCH
     dev_images = make_images(seed0, BATCH, device=dev)
-    host_images = make_images(seed0, BATCH, pin=True)
+    # end-to-end arm: host images as the reference's DatasetMapper delivers them -- uint8 BGR [3,H,W] tensors
+    # (detectron2/data/dataset_mapper.py: torch.as_tensor(image.transpose(2, 0, 1))), here in pinned memory
+    host_images = [im.to(torch.uint8).pin_memory() for im in make_images(seed0, BATCH)]
     batched = [{"image": im, "height": H, "width": W} for im in host_images]
 
     def barrier():
@@ -393,7 +395,8 @@ def main():
                 "clocks": sampler.summary(),
                 "e2e": {"value": imgs / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / K,
-                        "api": "lvc_b200.modeling.GeneralizedRCNN(batched_inputs) with pinned host fp32 images"},
+                        "api": "lvc_b200.modeling.GeneralizedRCNN(batched_inputs), pinned host uint8 [3,800,1333] images (DatasetMapper format), "
+                               "H2D + forward + packed D2H of the detections every step"},
                 "gpu_launches": launches_per_step * K,
                 "roofline": roof}
         line.update(extras)

@@ -276,8 +276,55 @@ def gold_corrector():
     save("box_corrector", **out)
 
 
+def gold_candidates():
+    """get_ret_anns (tools/create_coco_dataset_from_dets_all.py:129-193) in score mode and top-K mode, with and without --full,
+    on a synthetic detection set.  pycocotools is absent: the shim supplies a minimal COCO index with pycocotools' semantics."""
+    import importlib
+    import types
+    sys.argv = ["x", "--dt-path", "none", "--K-min", "0", "--K-max", "1"]
+    tool = importlib.import_module("tools.create_coco_dataset_from_dets_all")
+    rng = np.random.default_rng(17)
+    n_img, n = 40, 1500
+    imgs = [{"id": 1000 + i, "height": int(rng.integers(300, 800)), "width": int(rng.integers(300, 1000))} for i in range(n_img)]
+    novel = [3, 7, 11]
+    cats = [{"id": c, "name": str(c)} for c in range(15)]
+    anns = []
+    for k in range(n):
+        im = imgs[int(rng.integers(0, n_img))]
+        w, h = float(rng.uniform(1, im["width"] * 1.05)), float(rng.uniform(1, im["height"] * 1.05))
+        if k % 97 == 0:
+            w = 0.0                                    # zero-area detection
+        anns.append({"id": k + 1, "image_id": im["id"], "category_id": int(rng.integers(0, 15)), "bbox": [0.0, 0.0, w, h],
+                     "area": w * h, "score": float(np.float32(rng.uniform(0, 1))), "iscrowd": 0})
+    train_imgs = {c: set(int(v) for v in rng.choice([i["id"] for i in imgs], 6, replace=False)) for c in novel}
+    out = dict(image_id=np.array([a["image_id"] for a in anns]), category=np.array([a["category_id"] for a in anns]),
+               score=np.array([a["score"] for a in anns], np.float32), area=np.array([a["area"] for a in anns]),
+               image_area=np.array([next(i for i in imgs if i["id"] == a["image_id"]) for a in anns] and
+                                   [float(next(i for i in imgs if i["id"] == a["image_id"])["height"]) *
+                                    float(next(i for i in imgs if i["id"] == a["image_id"])["width"]) for a in anns]),
+               novel=np.array(novel), train_keys=np.array(novel),
+               **{f"train_{c}": np.array(sorted(train_imgs[c])) for c in novel})
+    for tag, kw in (("score_full", dict(top=False, full=True, K_min=0.8, K_max=1.0, ar=0.0)),
+                    ("score_nofull", dict(top=False, full=False, K_min=0.5, K_max=0.9, ar=0.05)),
+                    ("top_full", dict(top=True, full=True, K_min=25, K_max=3, ar=0.0))):
+        import copy
+        coco = tool.COCO_PK()
+        coco.dataset = {"images": copy.deepcopy(imgs), "annotations": copy.deepcopy(anns), "categories": cats}
+        coco.createIndex()
+        args = types.SimpleNamespace(**kw)
+        ret = tool.get_ret_anns(coco, train_imgs, args, novel)
+        flags = np.zeros(n, np.int8)
+        for a in ret:
+            flags[a["id"] - 1] = 2 if a.get("ignore_qe", 0) == 1 else 1
+        out["flags_" + tag] = flags
+        print(tag, "kept", int((flags == 1).sum()), "ignore", int((flags == 2).sum()))
+    save("candidates", **out)
+
+
 def main():
-    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector"]
+    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector", "cand"]
+    if "cand" in which:
+        gold_candidates()
     if "nms" in which:
         gold_batched_nms()
     if "pooler" in which:

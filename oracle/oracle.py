@@ -319,3 +319,36 @@ def knn_reference_form_torch(bank, bank_cls, queries, per_call=5, topk=10):
         sim = F.cosine_similarity(bank.sub(crop_mean).unsqueeze(0).float(), qf.sub(crop_mean).unsqueeze(1).float(), dim=-1)
         out.append(bcls[sim.topk(topk, dim=-1)[1]])
     return torch.cat(out).numpy()
+
+
+# ------------------------------------------------------------------------------------ candidate filter (a15)
+def select_candidates(image_id, category, score, area, image_area, train_imgs, novel_classes, k_min, k_max, ar=0.0, full=True,
+                      top=False):
+    """get_ret_anns, tools/create_coco_dataset_from_dets_all.py:129-193, on flat arrays (one entry per detection, in
+    annotation-id order).  train_imgs: dict class -> set(image ids holding that class's few-shot GT).
+    Returns flags [n] int8: 0 = dropped, 1 = pseudo-label candidate (ignore_qe=0, iscrowd=0), 2 = ignore region
+    (ignore_qe=1, iscrowd=1; only with ``full``).  Score mode keeps K_min < score <= K_max (left searchsorted on -scores,
+    :169-174); top mode keeps ranks [K_max, K_min) of the per-class descending-score list (:143-149)."""
+    n = len(score)
+    flags = np.zeros(n, np.int8)
+    image_id, category = np.asarray(image_id), np.asarray(category)
+    score, area, image_area = _f32(score).astype(np.float64), np.asarray(area, np.float64), np.asarray(image_area, np.float64)
+    ratio = area / image_area
+    for cid in novel_classes:
+        excl = train_imgs.get(cid, set())
+        valid = [i for i in range(n) if category[i] == cid and image_id[i] not in excl and 0.0 < area[i] < 1e10
+                 and ar < ratio[i] < 1.0]
+        order = sorted(valid, key=lambda i: score[i], reverse=True)       # python's sort is stable, like the reference's
+        if top:
+            keep = order[int(k_max):int(k_min)]
+        else:
+            sc = np.array([score[i] for i in order])
+            keep = order[int(np.searchsorted(-sc, -float(k_max))):int(np.searchsorted(-sc, -float(k_min)))]
+        for i in keep:
+            flags[i] = 1
+        if full:
+            pres = set(image_id[i] for i in keep)
+            for i in valid:
+                if image_id[i] in pres and flags[i] != 1:
+                    flags[i] = 2
+    return flags

@@ -236,6 +236,56 @@ def _make_weight_init():
     return m
 
 
+class _MiniCOCO:
+    """The subset of pycocotools.coco.COCO (v2.0) that tools/create_coco_dataset_from_dets_all.py touches: createIndex,
+    getImgIds, getAnnIds (imgIds / catIds / areaRng / iscrowd filters), loadAnns.  Semantics follow pycocotools' coco.py."""
+
+    def __init__(self, annotation_file=None):
+        self.dataset, self.anns, self.cats, self.imgs = {}, {}, {}, {}
+        self.imgToAnns, self.catToImgs = {}, {}
+        if annotation_file is not None:
+            import json
+            self.dataset = json.load(open(annotation_file)) if isinstance(annotation_file, str) else annotation_file
+            self.createIndex()
+
+    def createIndex(self):
+        from collections import defaultdict
+        anns, cats, imgs = {}, {}, {}
+        imgToAnns, catToImgs = defaultdict(list), defaultdict(list)
+        for ann in self.dataset.get("annotations", []):
+            imgToAnns[ann["image_id"]].append(ann)
+            anns[ann["id"]] = ann
+            catToImgs[ann["category_id"]].append(ann["image_id"])
+        for img in self.dataset.get("images", []):
+            imgs[img["id"]] = img
+        for cat in self.dataset.get("categories", []):
+            cats[cat["id"]] = cat
+        self.anns, self.imgToAnns, self.catToImgs, self.imgs, self.cats = anns, imgToAnns, catToImgs, imgs, cats
+
+    def getImgIds(self, imgIds=[], catIds=[]):
+        return list(self.imgs.keys())
+
+    def getAnnIds(self, imgIds=[], catIds=[], areaRng=[], iscrowd=None):
+        imgIds = imgIds if isinstance(imgIds, (list, tuple)) else [imgIds]
+        catIds = catIds if isinstance(catIds, (list, tuple)) else [catIds]
+        if len(imgIds) == len(catIds) == len(areaRng) == 0:
+            anns = self.dataset["annotations"]
+        else:
+            if len(imgIds) != 0:
+                import itertools
+                anns = list(itertools.chain.from_iterable(self.imgToAnns[i] for i in imgIds if i in self.imgToAnns))
+            else:
+                anns = self.dataset["annotations"]
+            anns = anns if len(catIds) == 0 else [a for a in anns if a["category_id"] in catIds]
+            anns = anns if len(areaRng) == 0 else [a for a in anns if a["area"] > areaRng[0] and a["area"] < areaRng[1]]
+        if iscrowd is not None:
+            return [a["id"] for a in anns if a["iscrowd"] == iscrowd]
+        return [a["id"] for a in anns]
+
+    def loadAnns(self, ids=[]):
+        return [self.anns[i] for i in ids] if isinstance(ids, (list, tuple)) else [self.anns[ids]]
+
+
 class _PathManager:
     @staticmethod
     def open(path, mode="r", **kw):
@@ -301,6 +351,8 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             m.__all__ = names
         elif name == "termcolor":
             m.colored = lambda s, *a, **k: s
+        elif name == "pycocotools.coco":
+            m.COCO = _MiniCOCO
         return m
 
     def exec_module(self, module):
