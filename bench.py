@@ -367,10 +367,15 @@ def main():
                     f.write(f"M={M_} N={N_} K={K_} ms={t_:.4f} TFLOPs(padded)={2 * M_ * N_ * K_ / t_ / 1e9:.1f}\n")
             ops.GEMM_EVENTS = None
         eng.use_cuda_graph = use_graph
+        traffic = None   # DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/)
+        tp = os.path.join(ROOT, "profiles", "r01_gemm_step_metrics.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         alg_tflop = algorithmic_gflop_per_image(cfg) * BATCH / 1e3
         ach = alg_tflop / (gemm_ms / 1e3)
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all dense layers: 104 backbone convs, FPN, RPN head, box head)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_note": "mean dram__bytes_read+write per GEMM launch over the 125 launches of one step (ncu, profiles/r01_gemm_step_metrics.json)",
                 "peak_source": f"{which} (sustained bf16, MEASURED_PEAKS.json)", "launches": n_gemm,
                 "timing": "the step's GEMM launches replayed back to back in a CUDA graph, CUDA events, mean of K replays",
                 "avg_launch_ms": gemm_ms / max(n_gemm, 1), "gemm_ms_per_step": gemm_ms, "algorithmic_tflop_per_step": alg_tflop,

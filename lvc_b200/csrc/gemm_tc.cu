@@ -13,6 +13,7 @@
 // warps 4..7 epilogue (TMEM lane quadrant = warp % 4).  Two TMEM accumulator buffers let the epilogue of tile i
 // overlap the main loop of tile i+1.  Tile = 128 x BLOCK_N, BLOCK_K = 64 (one 128-byte swizzle row).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -248,12 +249,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * p.k_elems, n0);
           }
         }
-        if (p.has_res) {   // residual [128 x 64] tiles as extra A operands
-          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j++, it++) {
+        if (p.has_res) {   // residual [128 x 64] tiles as extra A operands; a stage carries two of them (A slot + B slot)
+          constexpr int kResPerStage = (BLOCK_N >= 128) ? 2 : 1;
+          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j += kResPerStage, it++) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+            const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < p.N);
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * s, kStageBytesA);
+            mbar_arrive_expect_tx(bar_full + 8 * s, two ? 2 * kStageBytesA : kStageBytesA);
             tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_r, bar_full + 8 * s, n0 + j * 64, m0);
+            if (two) tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_r, bar_full + 8 * s, n0 + (j + 1) * 64, m0);
           }
         }
       }
@@ -289,14 +293,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         if (p.has_res) {
           if constexpr (BLOCK_N >= 64) {
-            for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j++, it++) {
+            constexpr int kResPerStage = (BLOCK_N >= 128) ? 2 : 1;
+            for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j += kResPerStage, it++) {
               const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+              const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < p.N);
               mbar_wait(bar_full + 8 * s, ph);
               tc_fence_after();
               const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * kStageBytesA);
+              const uint64_t adesc2 = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; k++)
                 umma_bf16(tmem_d + j * 64, adesc + 2 * k, ident_desc + 2 * k, idesc_res, 1u);   // D[:, 64j:64j+64] += R_tile * I
+              if (two) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+                  umma_bf16(tmem_d + (j + 1) * 64, adesc2 + 2 * k, ident_desc + 2 * k, idesc_res, 1u);
+              }
               umma_commit(bar_empty + 8 * s);
             }
           }
@@ -509,7 +521,11 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   LVC_REQUIRE(d->M < (1ll << 31) && d->M_rows < (1ll << 31), "gemm: M too large");
   int bn = d->N >= 256 ? 256 : (d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16)));
   if (d->N > 128 && d->N < 256) bn = 256;
-  if (tf32) bn = d->N > 128 ? 256 : 128;   // fp32 operands double the smem bytes per MMA: wide tiles keep B traffic per flop low
+  if (tf32) bn = d->N > 128 ? 256 : 128;
+  {
+    static const char* e_bn = getenv("LVCB200_GEMM_BN");
+    if (e_bn && !tf32 && d->N >= atoi(e_bn) && atoi(e_bn) >= 64) bn = atoi(e_bn);
+  }   // fp32 operands double the smem bytes per MMA: wide tiles keep B traffic per flop low
   // epilogue mode: fp32 output -> direct stores from registers; bf16 output -> smem staging + TMA stores
   const int mode = d->d_dtype == LVCB200_F32 ? 0 : 1;
   if ((mode == 1 || d->residual) && bn < 64) bn = 64;
@@ -538,6 +554,13 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   }
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (!deep && p.num_stages > 4) p.num_stages = 4;
+  {  // tuning overrides for experiments (tools/gemm_sweep.py); not used by the engine
+    static const char* e_st = getenv("LVCB200_GEMM_STAGES");
+    static const char* e_ph = getenv("LVCB200_GEMM_PHASE");
+    if (e_ph && mode == 1) p.phase_cols = atoi(e_ph) > bn ? bn : atoi(e_ph);
+    if (e_st) p.num_stages = atoi(e_st);
+    while (p.num_stages > 2 && gemm_smem_bytes(bn, mode, p.num_stages, p.phase_cols, p.has_res) > 232448) p.num_stages--;
+  }
   LVC_REQUIRE(p.num_stages >= 2, "gemm: internal: pipeline too shallow");
   CUtensorMap ta, tw, td, tr;
   int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M, tf32);
