@@ -19,12 +19,22 @@ namespace lvcb200 {
 
 constexpr int QT = 32, BT = 128, KT = 32, KNN_MAXK = 16;
 
-__global__ void knn_mean_kernel(const float* __restrict__ bank, int S, int D, float* __restrict__ mean) {
-  int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
+// column mean of the bank (crop_mean): 32 columns per CTA, 8 warps stride the rows, double accumulation
+__global__ void __launch_bounds__(256)
+knn_mean_kernel(const float* __restrict__ bank, int S, int D, float* __restrict__ mean) {
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
   double a = 0.0;
-  for (int s = 0; s < S; s++) a += (double)bank[(size_t)s * D + d];
-  mean[d] = (float)(a / (double)S);
+  if (d < D)
+    for (int s = w; s < S; s += 8) a += (double)bank[(size_t)s * D + d];
+  part[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && d < D) {
+    double t = 0.0;
+    for (int i = 0; i < 8; i++) t += part[i][lane];
+    mean[d] = (float)(t / (double)S);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -211,20 +221,21 @@ knn_rerank_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
     // fp32 accumulation, fp16 output rounding (2^-11 |score|, |score| <= |q - mu|); 30 % slack
     const float eps = 0.0026f * norm_q + 0.0007f * norm_qc + 1e-6f;
     __syncwarp();
-    // (c) k-th largest approximate score: k rounds of "next element in (value desc, index asc) order"
-    float cur_v = INFINITY; int cur_i = -1;
-    for (int round = 0; round < topk; round++) {
-      float bv = -INFINITY; int bi = 0x7fffffff;
-      for (int i = lane; i < S; i += 32) {
-        float v = __half2float(ssc[i]);
-        bool after = (v < cur_v) || (v == cur_v && i > cur_i);
-        if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    // (c) a lower bound of the k-th largest approximate score: the k-th largest of the 32 per-lane maxima (the k-th largest
+    //     of any subset is <= the k-th largest of the whole row), found by rank counting over the warp.  Any lower bound keeps
+    //     the candidate rule rigorous; this one typically sits 2-3 ranks below the exact k-th value.
+    float cur_v;
+    {
+      float lm = -INFINITY;
+      for (int i = lane; i < S; i += 32) lm = fmaxf(lm, __half2float(ssc[i]));
+      int rank = 0;
+      for (int o = 0; o < 32; o++) {
+        float ov = __shfl_sync(0xffffffffu, lm, o);
+        rank += (ov > lm) || (ov == lm && o < lane);
       }
-      for (int o = 16; o; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      cur_v = bv; cur_i = bi;
+      const int want = (topk - 1) < 31 ? (topk - 1) : 31;
+      unsigned int m = __ballot_sync(0xffffffffu, rank == want);
+      cur_v = __shfl_sync(0xffffffffu, lm, __ffs(m) - 1);
     }
     const float tau = cur_v - 2.f * eps;
     // (d) candidate set
@@ -263,26 +274,49 @@ knn_rerank_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
     }
     __syncwarp();
     // (f) exact top-k among the candidates (sim desc, index asc), votes, mode, keep
-    float pv = INFINITY; int pi = -1;
     int64_t myvote = -1;   // lane r keeps the vote of rank r
-    for (int round = 0; round < topk; round++) {
-      float bv = -INFINITY; int bi = 0x7fffffff;
-      for (int j = lane; j < nc; j += 32) {
-        float v = csim[j]; int i = cidx[j];
-        bool after = (v < pv) || (v == pv && i > pi);
-        if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    if (nc <= 32) {        // one candidate per lane: rank by counting, rank r writes output slot r
+      const float mv = lane < nc ? csim[lane] : -INFINITY;
+      const int mi = lane < nc ? cidx[lane] : 0x7fffffff;
+      int rank = 0;
+      for (int o = 0; o < nc; o++) {
+        float ov = __shfl_sync(0xffffffffu, mv, o); int oi = __shfl_sync(0xffffffffu, mi, o);
+        rank += (ov > mv) || (ov == mv && oi < mi);
       }
-      for (int o = 16; o; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      const bool out_lane = lane < nc && rank < topk;
+      const int64_t vote = out_lane ? bank_cls[mi] : -1;
+      if (out_lane) {
+        top_idx[q * topk + rank] = mi;
+        votes[q * topk + rank] = vote;
+        if (top_sim) top_sim[q * topk + rank] = mv;
       }
-      pv = bv; pi = bi;
-      const int64_t vote = (bi != 0x7fffffff) ? bank_cls[bi] : -1;
-      if (lane == round) myvote = vote;
-      if (lane == 0) {
-        top_idx[q * topk + round] = (bi != 0x7fffffff) ? bi : -1;
-        votes[q * topk + round] = vote;
-        if (top_sim) top_sim[q * topk + round] = bv;
+      // move the vote of rank r to lane r
+      for (int r2 = 0; r2 < topk; r2++) {
+        unsigned int m = __ballot_sync(0xffffffffu, out_lane && rank == r2);
+        int64_t v = __shfl_sync(0xffffffffu, vote, m ? __ffs(m) - 1 : 0);
+        if (lane == r2) myvote = m ? v : -1;
+      }
+    } else {
+      float pv = INFINITY; int pi = -1;
+      for (int round = 0; round < topk; round++) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int j = lane; j < nc; j += 32) {
+          float v = csim[j]; int i = cidx[j];
+          bool after = (v < pv) || (v == pv && i > pi);
+          if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+        }
+        for (int o = 16; o; o >>= 1) {
+          float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        pv = bv; pi = bi;
+        const int64_t vote = (bi != 0x7fffffff) ? bank_cls[bi] : -1;
+        if (lane == round) myvote = vote;
+        if (lane == 0) {
+          top_idx[q * topk + round] = (bi != 0x7fffffff) ? bi : -1;
+          votes[q * topk + round] = vote;
+          if (top_sim) top_sim[q * topk + round] = bv;
+        }
       }
     }
     // torch.mode over the first knn votes: most frequent, smallest value on ties
@@ -316,7 +350,7 @@ extern "C" int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_p
   float* mean = (float*)bank_prepared;
   float* negc = mean + D;
   float* bhat = negc + knn_s_al(S);
-  knn_mean_kernel<<<(D + 255) / 256, 256, 0, s>>>(bank, S, D, mean);
+  knn_mean_kernel<<<(D + 31) / 32, 256, 0, s>>>(bank, S, D, mean);
   int rc = check_launch("knn_mean_kernel");
   if (rc) return rc;
   knn_normalize_kernel<<<knn_s_pad(S), 256, 0, s>>>(bank, S, D, mean, bhat, negc);

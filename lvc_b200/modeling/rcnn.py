@@ -40,6 +40,45 @@ class GeneralizedRCNN:
         return self.inference(batched_inputs)
 
     @torch.no_grad()
+    def inference_stream(self, batches):
+        """Software-pipelined form of the reference's inference loop (``for inputs in data_loader: outputs = model(inputs)``,
+        lvc/evaluation/evaluator.py:117-126): yields ``model(inputs)`` for every batch of the iterable, in order, while the
+        H2D copy of batch i+1 (copy stream) overlaps the forward of batch i and the packed D2H of its detections."""
+        copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        pending = None   # (host tensor, event, outs, k, keepalive)
+        for batched_inputs in batches:
+            with torch.cuda.stream(copy_stream):
+                images = self.to_device(batched_inputs)
+                ready = copy_stream.record_event()
+            sizes = [tuple(im.shape[-2:]) for im in images]
+            outs = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
+            main.wait_event(ready)
+            boxes, scores, classes, rows, counts = self.engine.run(images, outs)
+            packed = torch.cat([boxes.view(len(images), -1), scores, classes.float(), counts.float()[:, None]], dim=1)
+            host = torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True)
+            host.copy_(packed, non_blocking=True)
+            done = main.record_event()
+            if pending is not None:
+                yield self._unpack(*pending[:4])
+            pending = (host, done, outs, scores.shape[1], images)
+        if pending is not None:
+            yield self._unpack(*pending[:4])
+
+    @staticmethod
+    def _unpack(host, done, outs, k):
+        done.synchronize()
+        res = []
+        for i, o in enumerate(outs):
+            c = int(host[i, -1])
+            inst = Instances(o)
+            inst.pred_boxes = Boxes(host[i, : 4 * k].view(k, 4)[:c].clone())
+            inst.scores = host[i, 4 * k: 5 * k][:c].clone()
+            inst.pred_classes = host[i, 5 * k: 6 * k][:c].to(torch.int64)
+            res.append({"instances": inst})
+        return res
+
+    @torch.no_grad()
     def inference(self, batched_inputs: List[dict], do_postprocess=True):
         images = self.to_device(batched_inputs)
         sizes = [tuple(im.shape[-2:]) for im in images]

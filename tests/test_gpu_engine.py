@@ -194,3 +194,19 @@ def test_box_corrector_vs_golden_and_oracle(golden):
     finally:
         OM._EMULATE_BF16 = False
     assert np.abs(got - ref[0]).max() < 0.1
+
+
+def test_inference_stream_equals_blocking_calls():
+    cfg = DetectorConfig(depth=50)
+    sd = synthetic_state_dict(cfg, 0)
+    model = GeneralizedRCNN(cfg, sd, use_cuda_graph=True)
+    batches = [[{"image": (im * 1).to(torch.uint8), "height": 200, "width": 260} for im in _images(20 + 2 * b, [(192, 256), (192, 256)])]
+               for b in range(4)]
+    want = [model(b) for b in batches]
+    got = list(model.inference_stream(batches))
+    assert len(got) == len(want)
+    for w, g in zip(want, got):
+        for a, b in zip(w, g):
+            assert torch.equal(a["instances"].pred_boxes.tensor, b["instances"].pred_boxes.tensor)
+            assert torch.equal(a["instances"].scores, b["instances"].scores)
+            assert torch.equal(a["instances"].pred_classes, b["instances"].pred_classes)
