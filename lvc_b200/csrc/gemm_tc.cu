@@ -156,6 +156,7 @@ struct GemmParams {
   int has_res;                     // residual tile added on the tensor core: D += R_tile * I (identity B operand)
   int num_stages;                  // smem pipeline depth (runtime: deep for big-K layers, shallow + big staging for small-K)
   int phase_cols;                  // MODE 1: output columns staged per TMA-store phase (64 or 128)
+  int debug;                       // experiments only: 1 = issue no MMAs, 2 = issue no TMA loads (results are garbage)
 };
 
 // MODE 0: epilogue stores straight from registers (fp32 heads, tiny N).
@@ -244,6 +245,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int kb = 0; kb < p.k_blocks; kb++, it++) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            if (p.debug == 2) { mbar_arrive(bar_full + 8 * s); continue; }
             mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
             tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_a, bar_full + 8 * s, kb * p.k_elems, m0 + p.shift[t]);
             tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * p.k_elems, n0);
@@ -286,6 +288,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint64_t bdesc = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++) {  // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
+            if (p.debug == 1 && (ki > 0 || k > 0)) continue;
             if constexpr (KIND == 1) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
           }
@@ -554,7 +557,10 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   }
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (!deep && p.num_stages > 4) p.num_stages = 4;
+  p.debug = 0;
   {  // tuning overrides for experiments (tools/gemm_sweep.py); not used by the engine
+    static const char* e_dbg = getenv("LVCB200_GEMM_DEBUG");
+    if (e_dbg) p.debug = atoi(e_dbg);
     static const char* e_st = getenv("LVCB200_GEMM_STAGES");
     static const char* e_ph = getenv("LVCB200_GEMM_PHASE");
     if (e_ph && mode == 1) p.phase_cols = atoi(e_ph) > bn ? bn : atoi(e_ph);

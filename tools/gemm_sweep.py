@@ -42,8 +42,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         bench(f"{tag} c2 3x3 K={9 * bott} N={bott}", lambda: ops.gemm(y1, w2, bias=b1, out=y2, relu=True, taps=9, shifts=sh, K=bott, plane_hw=(PH, PW)))
         bench(f"{tag} c3 1x1+res K={bott} N={cout}", lambda: ops.gemm(y2, w3, bias=b3, residual=x, out=o, relu=True, plane_hw=(PH, PW)))
 else:
-    for env in [{}, {"LVCB200_GEMM_BN": "128"}, {"LVCB200_GEMM_PHASE": "64"}, {"LVCB200_GEMM_STAGES": "2"}, {"LVCB200_GEMM_STAGES": "3"},
-                {"LVCB200_GEMM_BN": "128", "LVCB200_GEMM_PHASE": "64"}, {"LVCB200_GEMM_BN": "64"}]:
+    configs = [{}, {"LVCB200_GEMM_BN": "128"}, {"LVCB200_GEMM_PHASE": "64"}, {"LVCB200_GEMM_STAGES": "2"}, {"LVCB200_GEMM_STAGES": "3"},
+               {"LVCB200_GEMM_BN": "128", "LVCB200_GEMM_PHASE": "64"}, {"LVCB200_GEMM_BN": "64"}]
+    if len(sys.argv) > 1 and sys.argv[1] == "debug":
+        configs = [{}, {"LVCB200_GEMM_DEBUG": "1"}, {"LVCB200_GEMM_DEBUG": "2"}, {"LVCB200_GEMM_BN": "64"},
+                   {"LVCB200_GEMM_BN": "64", "LVCB200_GEMM_DEBUG": "1"}, {"LVCB200_GEMM_BN": "64", "LVCB200_GEMM_DEBUG": "2"}]
+    for env in configs:
         print("== config", env or "default", flush=True)
         e = dict(os.environ)
         e.update(env)
