@@ -238,28 +238,38 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {  // ===================================== TMA producer
-      uint32_t it = 0;
+      // stage / phase advance incrementally: the stage count is a run-time value, and an integer modulo per K step was
+      // the critical path of this single-thread loop (profiles: ~500 cycles per K iteration regardless of tile width)
+      uint32_t stage = 0, phase = 0;
+      const int n_tiles = p.n_tiles, k_blocks = p.k_blocks, taps = p.taps, k_elems = p.k_elems, Kdim = p.K, Ndim = p.N;
+      const bool has_res = p.has_res != 0, no_tma = p.debug == 2;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
-        for (int t = 0; t < p.taps; t++) {
-          for (int kb = 0; kb < p.k_blocks; kb++, it++) {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-            if (p.debug == 2) { mbar_arrive(bar_full + 8 * s); continue; }
-            mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
-            tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_a, bar_full + 8 * s, kb * p.k_elems, m0 + p.shift[t]);
-            tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_w, bar_full + 8 * s, t * p.K + kb * p.k_elems, n0);
+        const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+        for (int t = 0; t < taps; t++) {
+          const int row = m0 + p.shift[t];
+          const int wcol0 = t * Kdim;
+          for (int kb = 0; kb < k_blocks; kb++) {
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            if (no_tma) { mbar_arrive(fb); }
+            else {
+              mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+              tma_load_2d(smem_a0 + stage * kStageBytesA, &tmap_a, fb, kb * k_elems, row);
+              tma_load_2d(smem_b0 + stage * Cfg::kStageBytesB, &tmap_w, fb, wcol0 + kb * k_elems, n0);
+            }
+            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
           }
         }
-        if (p.has_res) {   // residual [128 x 64] tiles as extra A operands; a stage carries two of them (A slot + B slot)
+        if (has_res) {   // residual [128 x 64] tiles as extra A operands; a stage carries two of them (A slot + B slot)
           constexpr int kResPerStage = (BLOCK_N >= 128) ? 2 : 1;
-          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j += kResPerStage, it++) {
-            const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-            const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < p.N);
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * s, two ? 2 * kStageBytesA : kStageBytesA);
-            tma_load_2d(smem_a0 + s * kStageBytesA, &tmap_r, bar_full + 8 * s, n0 + j * 64, m0);
-            if (two) tma_load_2d(smem_b0 + s * Cfg::kStageBytesB, &tmap_r, bar_full + 8 * s, n0 + (j + 1) * 64, m0);
+          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j += kResPerStage) {
+            const uint32_t fb = bar_full + 8 * stage;
+            const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < Ndim);
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            mbar_arrive_expect_tx(fb, two ? 2 * kStageBytesA : kStageBytesA);
+            tma_load_2d(smem_a0 + stage * kStageBytesA, &tmap_r, fb, n0 + j * 64, m0);
+            if (two) tma_load_2d(smem_b0 + stage * Cfg::kStageBytesB, &tmap_r, fb, n0 + (j + 1) * 64, m0);
+            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -269,41 +279,44 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc = KIND == 1 ? make_idesc_tf32(BLOCK_M, BLOCK_N) : make_idesc_bf16(BLOCK_M, BLOCK_N);
       constexpr uint32_t idesc_res = make_idesc_bf16(BLOCK_M, 64);
       const uint64_t ident_desc = make_smem_desc_sw128(smem_base + off_ident);
-      uint32_t it = 0, tc = 0;
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_a0), bdesc0 = make_smem_desc_sw128(smem_b0);
+      uint32_t stage = 0, phase = 0, tc = 0;
+      const int n_tiles = p.n_tiles, Ndim = p.N;
+      const bool has_res = p.has_res != 0, no_mma = p.debug == 1;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
-        const int n0 = (tile % p.n_tiles) * BLOCK_N;
+        const int n0 = (tile % n_tiles) * BLOCK_N;
         const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
         mbar_wait(bar_tempty + 8 * b, bph ^ 1u);   // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + b * BLOCK_N;
         // a partial last N tile issues a narrower MMA (N rounded up to 16): no tensor-pipe time for padding columns
-        const int n_rem = p.N - n0;
+        const int n_rem = Ndim - n0;
         const int n_eff = n_rem >= BLOCK_N ? BLOCK_N : ((n_rem + 15) & ~15);
         const uint32_t idesc_t = (idesc & ~(0x3fu << 17)) | ((uint32_t)(n_eff >> 3) << 17);
-        for (int ki = 0; ki < k_iters; ki++, it++) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(bar_full + 8 * s, ph);
+        for (int ki = 0; ki < k_iters; ki++) {
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * kStageBytesA);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
+          // descriptors advance by whole stages in the (address >> 4) field
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * (kStageBytesA >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (Cfg::kStageBytesB >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++) {  // +32 bytes per K step inside the swizzle row => +2 in the >>4 address field
-            if (p.debug == 1 && (ki > 0 || k > 0)) continue;
+            if (no_mma && (ki > 0 || k > 0)) continue;
             if constexpr (KIND == 1) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * s);             // frees the smem slot once these MMAs have read it
+          umma_commit(bar_empty + 8 * stage);             // frees the smem slot once these MMAs have read it
+          if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
         }
-        if (p.has_res) {
+        if (has_res) {
           if constexpr (BLOCK_N >= 64) {
             constexpr int kResPerStage = (BLOCK_N >= 128) ? 2 : 1;
-            for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < p.N; j += kResPerStage, it++) {
-              const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-              const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < p.N);
-              mbar_wait(bar_full + 8 * s, ph);
+            for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j += kResPerStage) {
+              const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < Ndim);
+              mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
-              const uint64_t adesc = make_smem_desc_sw128(smem_a0 + s * kStageBytesA);
-              const uint64_t adesc2 = make_smem_desc_sw128(smem_b0 + s * Cfg::kStageBytesB);
+              const uint64_t adesc = adesc0 + (uint64_t)(stage * (kStageBytesA >> 4));
+              const uint64_t adesc2 = bdesc0 + (uint64_t)(stage * (Cfg::kStageBytesB >> 4));
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; k++)
                 umma_bf16(tmem_d + j * 64, adesc + 2 * k, ident_desc + 2 * k, idesc_res, 1u);   // D[:, 64j:64j+64] += R_tile * I
@@ -312,7 +325,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int k = 0; k < BLOCK_K / UMMA_K; k++)
                   umma_bf16(tmem_d + (j + 1) * 64, adesc2 + 2 * k, ident_desc + 2 * k, idesc_res, 1u);
               }
-              umma_commit(bar_empty + 8 * s);
+              umma_commit(bar_empty + 8 * stage);
+              if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -340,7 +354,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         unsigned int y = rem / (unsigned)p.plane_w, x = rem - y * (unsigned)p.plane_w;
         zero_row = (y == 0) || (y == (unsigned)p.plane_h - 1) || (x == 0) || (x == (unsigned)p.plane_w - 1);
       }
-      mbar_wait(bar_tfull + 8 * b, bph);
+      if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);   // one poller per warp keeps the mbarrier unit free for the TMA / MMA threads
+      __syncwarp();
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BLOCK_N;
       if constexpr (MODE == 0) {
