@@ -76,11 +76,32 @@ def algorithmic_gflop_per_image(cfg, n_props=1000):
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons DURING the timed regions (NVML; nvidia-smi as a fallback)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            try:
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for k, b in bits.items():
+                if r & b:
+                    self.reasons.add(k)
+            time.sleep(0.005)
+
+    def _smi_loop(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -97,10 +118,16 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_min_mhz": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
 
 
 def measured_peaks():

@@ -458,6 +458,259 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
+// ------------------------------------------------------------------------------------------ 2-CTA variant
+// CTA pairs (cluster of 2, same TPC) compute 256 x BLOCK_N tiles with tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of
+// A and HALF of the B tile, the leader CTA's elected thread issues one MMA for both SMs.  One instruction now carries 256 rows, so
+// narrow-N layers (the single-thread issue rate is ~128 cycles per MMA whatever N is -- tools/gemm_sweep.py) do twice the work per
+// issue slot, and every layer moves half the B bytes per SM.  bf16 operands, bf16 output (staged TMA stores), residual as identity MMA.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's barrier (local for the leader itself)
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+__host__ __device__ inline int gemm2_smem_bytes(int block_n, int num_stages, int phase_cols, int has_res) {
+  int b = num_stages * (kStageBytesA + (block_n / 2) * BLOCK_K * 2) + 2 * BLOCK_M * phase_cols * 2;
+  if (has_res) b += kIdentBytes / 2;
+  return b + kCtrlBytes + 1024;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+  constexpr int kHalfN = BLOCK_N / 2;
+  constexpr int kStageBytesBh = kHalfN * BLOCK_K * 2;
+  constexpr int kStageBytesCta = kStageBytesA + kStageBytesBh;
+  constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  const int kStages = p.num_stages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + kStages * kStageBytesA;
+  const uint32_t off_staging = kStages * kStageBytesCta;
+  const uint32_t staging_bytes = 2u * BLOCK_M * p.phase_cols * 2u;
+  const uint32_t off_ident = off_staging + staging_bytes;
+  const uint32_t off_ctrl = off_ident + (p.has_res ? kIdentBytes / 2 : 0);
+  uint8_t* ctrl = smem_al + off_ctrl;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 8 * (2 * kMaxStages + 4));
+  float* s_bias = reinterpret_cast<float*>(ctrl + 1024);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages, bar_tempty = bar_tfull + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_w); tma_prefetch_desc(&tmap_d);
+    if (p.has_res) tma_prefetch_desc(&tmap_r);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * (kEpiThreads / 32)); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_slot), kTmemCols);
+  if (p.has_res && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    // this CTA's half of the 64x64 identity B operand: rows n = 32*rank + nl, K-major, SWIZZLE_128B
+    uint8_t* ident = smem_al + off_ident;
+    const int t = threadIdx.x - kEpiWarp0 * 32;
+    for (int i = t; i < kIdentBytes / 2 / 16; i += 128) reinterpret_cast<uint4*>(ident)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t < 32) {
+      const int nl = t, k = 32 * (int)rank + nl, c = k >> 3;
+      *reinterpret_cast<__nv_bfloat16*>(ident + nl * 128 + ((c ^ (nl & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(1.0f);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // peer barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;       // m_tiles counts 256-row tiles here
+  const int k_iters = p.taps * p.k_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===================================== TMA producer (both CTAs: own A rows, own half of B)
+      uint32_t stage = 0, phase = 0;
+      const int n_tiles = p.n_tiles, k_blocks = p.k_blocks, taps = p.taps, Kdim = p.K, Ndim = p.N;
+      const bool has_res = p.has_res != 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+        for (int t = 0; t < taps; t++) {
+          const int row = m0 + p.shift[t];
+          const int wcol0 = t * Kdim;
+          for (int kb = 0; kb < k_blocks; kb++) {
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * kStageBytesCta);     // bytes of BOTH CTAs land on the leader's barrier
+            tma_load_2d_2sm(smem_a0 + stage * kStageBytesA, &tmap_a, fb, kb * BLOCK_K, row);
+            tma_load_2d_2sm(smem_b0 + stage * kStageBytesBh, &tmap_w, fb, wcol0 + kb * BLOCK_K, n0 + (int)rank * kHalfN);
+            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        if (has_res) {
+          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j++) {
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * kStageBytesA);
+            tma_load_2d_2sm(smem_a0 + stage * kStageBytesA, &tmap_r, fb, n0 + j * 64, m0);
+            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ======================== MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_res = make_idesc_bf16(2 * BLOCK_M, 64);
+      const uint64_t ident_desc = make_smem_desc_sw128(smem_base + off_ident);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_a0), bdesc0 = make_smem_desc_sw128(smem_b0);
+      uint32_t stage = 0, phase = 0, tc = 0;
+      const int n_tiles = p.n_tiles, Ndim = p.N;
+      const bool has_res = p.has_res != 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs, tc++) {
+        const int n0 = (tile % n_tiles) * BLOCK_N;
+        const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
+        mbar_wait(bar_tempty + 8 * b, bph ^ 1u);   // both CTAs' epilogues have drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + b * BLOCK_N;
+        for (int ki = 0; ki < k_iters; ki++) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * (kStageBytesA >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kStageBytesBh >> 4));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+            umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(bar_empty + 8 * stage);     // frees this stage in both CTAs
+          if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (has_res) {
+          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j++) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t adesc = adesc0 + (uint64_t)(stage * (kStageBytesA >> 4));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+              umma_bf16_2sm(tmem_d + j * 64, adesc + 2 * k, ident_desc + 2 * k, idesc_res, 1u);
+            umma_commit_2sm(bar_empty + 8 * stage);
+            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit_2sm(bar_tfull + 8 * b);           // accumulator complete -> epilogue warps of both CTAs
+      }
+    }
+  } else if (warp >= kEpiWarp0) {  // ========================= epilogue warps: this CTA's 128 rows
+    const int q = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    const int et = threadIdx.x - kEpiWarp0 * 32;
+    uint32_t tc = 0, gphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, tc++) {
+      const int m0 = (tile / p.n_tiles) * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
+      const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
+      for (int j = et; j < BLOCK_N; j += kEpiThreads) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      const long long m = (long long)m0 + q * 32 + lane;
+      bool zero_row = false;
+      if (p.plane_h > 0) {
+        unsigned int plane = (unsigned)(p.plane_h * p.plane_w);
+        unsigned int rem = (unsigned int)((unsigned long long)m % plane);
+        unsigned int y = rem / (unsigned)p.plane_w, x = rem - y * (unsigned)p.plane_w;
+        zero_row = (y == 0) || (y == (unsigned)p.plane_h - 1) || (x == 0) || (x == (unsigned)p.plane_w - 1);
+      }
+      if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BLOCK_N;
+      const int r = q * 32 + lane;
+      const int sw = r & 7;
+      const int cols_per_warp = p.phase_cols >> 1;
+#pragma unroll 1
+      for (int pc = 0; pc < BLOCK_N; pc += p.phase_cols) {
+        if (n0 + pc >= p.N) break;
+        const uint32_t buf_off = off_staging + (gphase & 1u) * (BLOCK_M * p.phase_cols * 2);
+        if (et == 0) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int c0 = pc + half * cols_per_warp;
+        if (n0 + c0 < p.N) {
+          uint32_t v[64];
+          tmem_ld32(taddr + c0, v);
+          if (cols_per_warp == 64) tmem_ld32(taddr + c0 + 32, v + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g2 = 0; g2 < 2; g2++) {
+            if (g2 * 32 >= cols_per_warp) break;
+            const int c = c0 + g2 * 32;
+            uint8_t* rowp = smem_al + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128) + r * 128;
+            const int hs = ((c - pc) >> 5) & 1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 8 * j + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                float a0 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e]) + bb[2 * e];
+                float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
+                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                if (zero_row) { a0 = 0.f; a1 = 0.f; }
+                ho[e] = __floats2bfloat162_rn(a0, a1);
+              }
+              *reinterpret_cast<uint4*>(rowp + (((hs * 4 + j) ^ sw) << 4)) = o;
+            }
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          for (int c = pc; c < pc + p.phase_cols && n0 + c < p.N; c += 64)
+            tma_store_2d(&tmap_d, smem_base + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128), n0 + c, m0);
+          tma_store_commit();
+        }
+        gphase++;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty + 8 * b);
+    }
+    if (et == 0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // nobody leaves while the pair may still signal into its shared memory
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, kTmemCols); }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -507,6 +760,31 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   return check_launch("gemm_bf16_tc_kernel");
+}
+
+template <int BLOCK_N>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
+                        cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int smem = gemm2_smem_bytes(BLOCK_N, p.num_stages, p.phase_cols, p.has_res);
+  if (smem > 232448) return set_error(LVCB200_EINVAL, "gemm: internal shared-memory budget exceeded (2-CTA)");
+  int tiles = p.m_tiles * p.n_tiles;
+  int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc2_kernel<BLOCK_N>, ta, tw, td, tr, p));
+  return check_launch("gemm_bf16_tc2_kernel");
 }
 
 template <int BLOCK_N>
@@ -592,6 +870,25 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (mode == 1 && (rc = make_tmap_2d(&td, d->D, d->M, d->N, d->ldd, BLOCK_M))) return rc;
   if (p.has_res && (rc = make_tmap_2d(&tr, d->residual, d->M, d->N, d->ldr, BLOCK_M))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    static const char* e_2 = getenv("LVCB200_GEMM_2CTA");
+    const int two_cta = e_2 ? atoi(e_2) : 0;
+    if (two_cta && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
+      GemmParams p2 = p;
+      p2.m_tiles = (int)((d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+      p2.phase_cols = bn >= 128 ? 128 : 64;
+      const int stage_bytes2 = kStageBytesA + (bn / 2) * BLOCK_K * 2;
+      p2.num_stages = (232448 - (kCtrlBytes + 1024) - 2 * BLOCK_M * p2.phase_cols * 2 - (p2.has_res ? kIdentBytes / 2 : 0)) / stage_bytes2;
+      if (p2.num_stages > kMaxStages) p2.num_stages = kMaxStages;
+      CUtensorMap tw2;
+      if ((rc = make_tmap_2d(&tw2, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn / 2))) return rc;
+      switch (bn) {
+        case 256: return launch_gemm2<256>(ta, tw2, td, tr, p2, s);
+        case 128: return launch_gemm2<128>(ta, tw2, td, tr, p2, s);
+        default: return launch_gemm2<64>(ta, tw2, td, tr, p2, s);
+      }
+    }
+  }
   if (tf32) return bn == 256 ? launch_gemm<256, 1, 1>(ta, tw, td, tr, p, s) : launch_gemm<128, 1, 1>(ta, tw, td, tr, p, s);
   switch (bn) {
     case 256: return launch_gemm_mode<256>(mode, ta, tw, td, tr, p, s);

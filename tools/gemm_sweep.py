@@ -44,6 +44,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
 else:
     configs = [{}, {"LVCB200_GEMM_BN": "128"}, {"LVCB200_GEMM_PHASE": "64"}, {"LVCB200_GEMM_STAGES": "2"}, {"LVCB200_GEMM_STAGES": "3"},
                {"LVCB200_GEMM_BN": "128", "LVCB200_GEMM_PHASE": "64"}, {"LVCB200_GEMM_BN": "64"}]
+    if len(sys.argv) > 1 and sys.argv[1] == "2cta":
+        configs = [{}, {"LVCB200_GEMM_2CTA": "1"}]
     if len(sys.argv) > 1 and sys.argv[1] == "debug":
         configs = [{}, {"LVCB200_GEMM_DEBUG": "1"}, {"LVCB200_GEMM_DEBUG": "2"}, {"LVCB200_GEMM_BN": "64"},
                    {"LVCB200_GEMM_BN": "64", "LVCB200_GEMM_DEBUG": "1"}, {"LVCB200_GEMM_BN": "64", "LVCB200_GEMM_DEBUG": "2"}]
