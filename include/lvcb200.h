@@ -230,6 +230,14 @@ int lvcb200_subsample2(const void* in, int n, int H, int W, int C, void* out, vo
 /* out += nearest-2x-upsample(top)  (FPN top-down path, fpn.py:131-133), zero-bordered bf16 planes. */
 int lvcb200_upsample2_add(const void* top, int n, int Ht, int Wt, int C, void* inout, int H, int W, void* stream);
 
+/* "Next" row: crop front end of the kNN descriptors.  Replaces get_crops_qe (lvc/data/utils.py:485-519) +
+ * preprocess_crops (tools/run_nearest_neighbours.py:102-105): image = planar [3,H,W] uint8 or fp32 on the device;
+ * geom [n,8] int32 per box = (y0, x0, actual_h, actual_w, top_pad, left_pad, padded_h, padded_w) as produced by
+ * lvc_b200.crops.crop_geometry (the python-slicing / get_padding rules of the reference); out [n,3,S,S] fp32,
+ * nearest-resized (F.interpolate mode='nearest') and normalised with mean / inv_std when given. */
+int lvcb200_crops_qe(const void* image, int image_dtype, int H, int W, const int32_t* geom, int n, int S, const float* mean,
+                     const float* inv_std, float* out, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -132,6 +132,30 @@ __global__ void upsample2_add_kernel(const uint4* __restrict__ top, int n, int H
   }
 }
 
+// get_crops_qe (lvc/data/utils.py:485-519) + preprocess_crops (tools/run_nearest_neighbours.py:102-105): per box, crop
+// (optionally with square context), zero-pad to a square, nearest-resize to S x S, (x - mean) / std.  Pure index arithmetic:
+// the crop geometry (python slicing clamps, get_padding's half-pixel rule) is computed per box on the host side of the call.
+struct CropGeom { int y0, x0, ah, aw, tp, lp, Hp, Wp; };   // source origin, actual crop extent, top/left padding, padded extent
+
+template <typename T>
+__global__ void crops_qe_kernel(const T* __restrict__ img, int H, int W, const CropGeom* __restrict__ geom, int n, int S,
+                                const float* __restrict__ mean, const float* __restrict__ inv_std, float* __restrict__ out) {
+  const long long total = (long long)n * 3 * S * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % S), oy = (int)((i / S) % S), c = (int)((i / ((long long)S * S)) % 3), b = (int)(i / ((long long)3 * S * S));
+    const CropGeom g = geom[b];
+    // F.interpolate(mode='nearest'): src = min(floor(dst * (in / out)), in - 1), scale in fp32
+    const float sy = (float)g.Hp / (float)S, sx = (float)g.Wp / (float)S;
+    int py = (int)floorf((float)oy * sy); py = py < g.Hp - 1 ? py : g.Hp - 1;
+    int px = (int)floorf((float)ox * sx); px = px < g.Wp - 1 ? px : g.Wp - 1;
+    const int cy = py - g.tp, cx = px - g.lp;          // position inside the (unpadded) crop
+    float v = 0.f;
+    if (cy >= 0 && cy < g.ah && cx >= 0 && cx < g.aw) v = (float)img[((long long)c * H + g.y0 + cy) * W + g.x0 + cx];
+    if (mean != nullptr) v = (v - mean[c]) * inv_std[c];
+    out[i] = v;
+  }
+}
+
 }  // namespace lvcb200
 
 using namespace lvcb200;
@@ -179,4 +203,19 @@ extern "C" int lvcb200_upsample2_add(const void* top, int n, int Ht, int Wt, int
   long long total = (long long)n * H * W * (C / 8);
   upsample2_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)top, n, Ht, Wt, C / 8, (uint4*)inout, H, W);
   return check_launch("upsample2_add_kernel");
+}
+
+extern "C" int lvcb200_crops_qe(const void* image, int image_dtype, int H, int W, const int32_t* geom /*device [n,8]*/, int n, int S,
+                                const float* mean, const float* inv_std, float* out, void* stream) {
+  if (n == 0) return 0;
+  LVC_REQUIRE(image && geom && out && H > 0 && W > 0 && S > 0, "crops_qe: bad argument");
+  LVC_REQUIRE((mean == nullptr) == (inv_std == nullptr), "crops_qe: mean and inv_std go together");
+  long long total = (long long)n * 3 * S * S;
+  if (image_dtype == LVCB200_U8)
+    crops_qe_kernel<unsigned char><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)image, H, W, (const CropGeom*)geom, n, S, mean, inv_std, out);
+  else if (image_dtype == LVCB200_F32)
+    crops_qe_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)image, H, W, (const CropGeom*)geom, n, S, mean, inv_std, out);
+  else
+    return set_error(LVCB200_EINVAL, "crops_qe: image dtype must be LVCB200_F32 or LVCB200_U8");
+  return check_launch("crops_qe_kernel");
 }

@@ -1,0 +1,129 @@
+"""Callers and wire format either side of the detection path, mirrored from the reference:
+
+* ``instances_to_coco_json``  -- lvc/evaluation/coco_evaluation.py:566-603 (XYXY -> XYWH, python lists, one dict per detection)
+* ``DatasetEvaluator`` / ``DatasetEvaluators`` / ``COCOResultCollector`` -- the reset / process / evaluate protocol of
+  lvc/evaluation/evaluator.py:13-82 and the prediction-gathering half of COCOEvaluator (coco_evaluation.py:96-147, 302-312)
+* ``inference_on_dataset``    -- lvc/evaluation/evaluator.py:85-161, same contract (returns ``evaluator.evaluate()``), but
+  the loop is software-pipelined through ``GeneralizedRCNN.inference_stream`` (H2D of batch i+1 overlaps the forward of batch i)
+  and there is no per-image ``cuda.synchronize()``; any batch size the loader yields is accepted (the reference pins 1).
+"""
+import datetime
+import itertools
+import json
+import logging
+import os
+import time
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+
+
+def instances_to_coco_json(instances, img_id):
+    """Dump an ``Instances`` to the reference's COCO-result dicts (coco_evaluation.py:566-603)."""
+    n = len(instances)
+    if n == 0:
+        return []
+    boxes = instances.pred_boxes.tensor.clone()
+    boxes[:, 2] -= boxes[:, 0]          # BoxMode.convert(XYXY_ABS -> XYWH_ABS), detectron2/structures/boxes.py:43-129
+    boxes[:, 3] -= boxes[:, 1]
+    boxes = boxes.tolist()
+    scores = instances.scores.tolist()
+    classes = instances.pred_classes.tolist()
+    return [{"image_id": img_id, "category_id": classes[k], "bbox": boxes[k], "score": scores[k]} for k in range(n)]
+
+
+class DatasetEvaluator:
+    def reset(self):
+        pass
+
+    def process(self, inputs, outputs):
+        pass
+
+    def evaluate(self):
+        pass
+
+
+class DatasetEvaluators(DatasetEvaluator):
+    def __init__(self, evaluators):
+        self._evaluators = evaluators
+
+    def reset(self):
+        for e in self._evaluators:
+            e.reset()
+
+    def process(self, inputs, outputs):
+        for e in self._evaluators:
+            e.process(inputs, outputs)
+
+    def evaluate(self):
+        results = OrderedDict()
+        for e in self._evaluators:
+            r = e.evaluate()
+            if r is not None and (not dist.is_initialized() or dist.get_rank() == 0):
+                for k, v in r.items():
+                    assert k not in results, f"Different evaluators produce results with the same key {k}"
+                    results[k] = v
+        return results
+
+
+class COCOResultCollector(DatasetEvaluator):
+    """The candidate-sourcing half of COCOEvaluator: collect per-image predictions, gather them on rank 0 in rank order
+    (== itertools.chain(*comm.gather(...)), coco_evaluation.py:119-126), write ``coco_instances_results.json`` with the
+    contiguous -> dataset category-id mapping applied (coco_evaluation.py:288-312)."""
+
+    def __init__(self, output_dir=None, contiguous_id_to_dataset_id=None, file_name="coco_instances_results.json"):
+        self._output_dir, self._map, self._file_name = output_dir, contiguous_id_to_dataset_id, file_name
+        self._predictions = []
+
+    def reset(self):
+        self._predictions = []
+
+    def process(self, inputs, outputs):
+        for inp, out in zip(inputs, outputs):
+            pred = {"image_id": inp["image_id"]}
+            if "instances" in out:
+                pred["instances"] = instances_to_coco_json(out["instances"].to("cpu"), inp["image_id"])
+            self._predictions.append(pred)
+
+    def evaluate(self):
+        preds = self._predictions
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+            dist.gather_object(preds, gathered, dst=0)
+            if dist.get_rank() != 0:
+                return {}
+            preds = list(itertools.chain(*gathered))
+        results = list(itertools.chain(*[p["instances"] for p in preds]))
+        if self._map is not None:
+            for r in results:
+                r["category_id"] = self._map[r["category_id"]]
+        if self._output_dir:
+            os.makedirs(self._output_dir, exist_ok=True)
+            with open(os.path.join(self._output_dir, self._file_name), "w") as f:
+                f.write(json.dumps(results))
+        return {"num_images": len(preds), "num_detections": len(results), "results": results}
+
+
+def inference_on_dataset(model, data_loader, evaluator):
+    """Same contract as the reference's ``inference_on_dataset``: runs ``model`` over ``data_loader`` (an iterable with a
+    length, yielding list[dict] batches), feeds every (inputs, outputs) pair to ``evaluator.process`` and returns
+    ``evaluator.evaluate()``; logs the reference's two timing lines."""
+    logger = logging.getLogger(__name__)
+    num_devices = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    total = len(data_loader)
+    logger.info("Start inference on {} batches".format(total))
+    evaluator.reset()
+    batches = list(data_loader) if not isinstance(data_loader, (list, tuple)) else data_loader
+    start = time.time()
+    n_img = 0
+    stream = model.inference_stream(batches) if hasattr(model, "inference_stream") else (model(b) for b in batches)
+    with torch.no_grad():
+        for inputs, outputs in zip(batches, stream):
+            evaluator.process(inputs, outputs)
+            n_img += len(inputs)
+    total_time = time.time() - start
+    logger.info("Total inference time: {} ({:.6f} s / img per device, on {} devices)".format(
+        str(datetime.timedelta(seconds=int(total_time))), total_time / max(n_img, 1), num_devices))
+    results = evaluator.evaluate()
+    return {} if results is None else results

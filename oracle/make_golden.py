@@ -321,10 +321,36 @@ def gold_candidates():
     save("candidates", **out)
 
 
+def gold_crops():
+    """get_crops_qe (lvc/data/utils.py:485-519), both operations, on a small image with edge-touching boxes (crop size 32)."""
+    import lvc.data.utils as U
+    import torch.nn.functional as F
+    from detectron2.structures import Boxes, Instances
+    rng = np.random.default_rng(18)
+    H, W = 60, 90
+    img = torch.from_numpy(rng.integers(0, 256, (1, 3, H, W)).astype(np.uint8))
+    boxes = np.array([[10, 12, 30, 40], [0, 0, 89, 59], [80, 50, 89, 59], [5, 5, 6, 30], [40, 20, 70, 21], [0, 30, 20, 59], [33, 7, 34, 8]],
+                     np.float32)
+    insts = []
+    for b in boxes:
+        i = Instances((H, W))
+        i.gt_boxes = Boxes(torch.from_numpy(b[None]))
+        insts.append(i)
+    out = dict(img=img[0], boxes=boxes.astype(np.int64))
+    orig = F.interpolate
+    for op in ("pad", "context"):
+        U.F.interpolate = lambda x, size, mode: orig(x.float(), (32, 32), mode=mode)      # the reference hard-codes 224; shrink the fixture
+        out["crops_" + op] = U.get_crops_qe(img, insts, operation=op)
+    U.F.interpolate = orig
+    save("crops", **out)
+
+
 def main():
-    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector", "cand"]
+    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector", "cand", "crops"]
     if "cand" in which:
         gold_candidates()
+    if "crops" in which:
+        gold_crops()
     if "nms" in which:
         gold_batched_nms()
     if "pooler" in which:

@@ -352,3 +352,41 @@ def select_candidates(image_id, category, score, area, image_area, train_imgs, n
                 if image_id[i] in pres and flags[i] != 1:
                     flags[i] = 2
     return flags
+
+
+# ------------------------------------------------------------------------------------ crops (next row f1)
+def get_crops_qe(img, boxes, operation="context", size=224):
+    """lvc/data/utils.py:485-519 restated with explicit loops: img [3,H,W], integer boxes [n,4] -> [n,3,size,size] float32."""
+    img = np.asarray(img)
+    _, H, W = img.shape
+
+    def get_padding(h, w):
+        max_d = max(h, w)
+        hp, vp = (max_d - w) / 2, (max_d - h) / 2
+        l = hp if hp % 1 == 0 else hp + 0.5
+        t = vp if vp % 1 == 0 else vp + 0.5
+        r = hp if hp % 1 == 0 else hp - 0.5
+        b = vp if vp % 1 == 0 else vp - 0.5
+        return int(l), int(r), int(t), int(b)
+
+    out = np.zeros((len(boxes), 3, size, size), np.float32)
+    for i, (x1, y1, x2, y2) in enumerate(np.asarray(boxes, np.int64).tolist()):
+        if operation == "pad":
+            l_p, r_p, t_p, b_p = get_padding(y2 - y1 + 1, x2 - x1 + 1)
+            crop = img[:, y1:y2 + 1, x1:x2 + 1]
+        else:
+            l_p, r_p, t_p, b_p = get_padding(y2 - y1 + 1, x2 - x1 + 1)
+            y1n, x1n = max(0, y1 - t_p), max(0, x1 - l_p)
+            y2n, x2n = min(H, y2 + b_p), min(W, x2 + r_p)
+            l_p, r_p, t_p, b_p = get_padding(y2n - y1n + 1, x2n - x1n + 1)
+            crop = img[:, y1n:y2n + 1, x1n:x2n + 1]
+        pad = np.zeros((3, crop.shape[1] + t_p + b_p, crop.shape[2] + l_p + r_p), np.float32)
+        pad[:, t_p:t_p + crop.shape[1], l_p:l_p + crop.shape[2]] = crop
+        Hp, Wp = pad.shape[1:]
+        sy, sx = np.float32(Hp) / np.float32(size), np.float32(Wp) / np.float32(size)
+        for oy in range(size):
+            py = min(int(np.floor(np.float32(oy) * sy)), Hp - 1)
+            for ox in range(size):
+                px = min(int(np.floor(np.float32(ox) * sx)), Wp - 1)
+                out[i, :, oy, ox] = pad[:, py, px]
+    return out
