@@ -232,6 +232,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, identity tile) ran while
+  // the previous kernel of the stream was still draining; its results are needed only from here on.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_blocks;
@@ -758,7 +762,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   if (smem > 232448) return set_error(LVCB200_EINVAL, "gemm: internal shared-memory budget exceeded");
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+  static const char* e_pdl = getenv("LVCB200_GEMM_PDL");
+  if (e_pdl == nullptr || atoi(e_pdl) != 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND>, ta, tw, td, tr, p));
+  } else {
+    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+  }
   return check_launch("gemm_bf16_tc_kernel");
 }
 
