@@ -210,3 +210,25 @@ def test_inference_stream_equals_blocking_calls():
             assert torch.equal(a["instances"].pred_boxes.tensor, b["instances"].pred_boxes.tensor)
             assert torch.equal(a["instances"].scores, b["instances"].scores)
             assert torch.equal(a["instances"].pred_classes, b["instances"].pred_classes)
+
+
+def test_edge_cases_tiny_image_and_no_detections():
+    """Smallest legal input (one 3x40x56 image -> padded 64x64, p6 = 1x1, fewer anchors than PRE_NMS_TOPK on every level) and a
+    score threshold nothing passes: the pipeline must return well-formed empty results, like the reference."""
+    cfg = DetectorConfig(depth=50, score_thresh_test=0.999)
+    sd = synthetic_state_dict(cfg, 0)
+    model = GeneralizedRCNN(cfg, sd, use_cuda_graph=False)
+    im = _images(5, [(40, 56)])[0]
+    res = model([{"image": im, "height": 80, "width": 112}])
+    inst = res[0]["instances"]
+    assert len(inst) == 0 and inst.image_size == (80, 112) and inst.pred_boxes.tensor.shape == (0, 4)
+    cfg2 = DetectorConfig(depth=50, score_thresh_test=0.0)
+    eng = DetectorEngine(cfg2, sd)
+    eng.debug = {}
+    boxes, scores, classes, rows, counts = eng.run([im.cuda()])
+    torch.cuda.synchronize()
+    c = int(eng.debug["prop_counts"][0])
+    assert 0 < c <= 1000 and int(counts[0]) > 0
+    col = {}
+    ref = OM.detector_forward(cfg2, sd, [im], device="cuda", collect=col, emulate_bf16=True)
+    assert abs(c - len(col["proposals"][0][0])) <= 0.1 * c + 3
