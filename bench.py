@@ -413,10 +413,16 @@ def main():
                 "gemm_share_of_step": gemm_ms / (ms / K)}
 
     extras = {}
-    if not args.no_extras:
-        extras["knn"] = knn_section(rank, world, dev, dist, with_cpu=(world == 1 and not args.no_cpu_baseline))
+    if not args.no_extras:   # secondary workloads (BASELINE configs #4, #5); a failure here must not lose the headline line
+        try:
+            extras["knn"] = knn_section(rank, world, dev, dist, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as e:  # noqa: BLE001
+            extras["knn"] = {"error": repr(e)}
         if rank == 0 and world == 1:
-            extras["box_corrector"] = corrector_section(dev)
+            try:
+                extras["box_corrector"] = corrector_section(dev)
+            except Exception as e:  # noqa: BLE001
+                extras["box_corrector"] = {"error": repr(e)}
 
     if rank == 0:
         imgs = world * BATCH * K
