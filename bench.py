@@ -241,6 +241,68 @@ def corrector_section(dev):
             "tflops": flop / (ms / 1e3) / 1e12, "frac_of_peak": flop / (ms / 1e3) / 1e12 / peak_tf}
 
 
+def ops_section(dev):
+    """Op-level numbers for the HBM/latency-bound kernels on COCO-shaped synthetic boxes: achieved GB/s =
+    algorithmic bytes / CUDA-event time of 10 back-to-back launches."""
+    import numpy as np
+    from lvc_b200 import ops
+    from lvc_b200.testing import coco_like_boxes
+    _, peak_hbm, _ = measured_peaks()
+    rng = np.random.default_rng(0)
+    N, P = BATCH, 1000
+    out = {}
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # --- fused multi-level RoIAlign (a9/a10): 8 x 1000 RoIs, 256-ch bf16 planes of an 800x1344 input
+    sizes = [(200, 336), (100, 168), (50, 84), (25, 42)]
+    g = torch.Generator(device=dev).manual_seed(0)
+    planes = []
+    for h, w in sizes:
+        t = torch.zeros((N, h + 2, w + 2, 256), dtype=torch.bfloat16, device=dev)
+        t[:, 1:h + 1, 1:w + 1] = torch.randn((N, h, w, 256), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+        planes.append(ops.Plane(t, h, w, 256))
+    boxes = np.concatenate([np.concatenate([np.full((P, 1), i, np.float32), coco_like_boxes(rng, P)], 1) for i in range(N)])
+    rois = torch.from_numpy(boxes).to(dev)
+    scales = [0.25, 0.125, 0.0625, 0.03125]
+    ms = timed(lambda: ops.roi_pool_fpn(planes, scales, rois, out_dtype=torch.bfloat16, out_layout=ops.OUT_NHWC))
+    alg = N * (P * 256 * 49 * 2 + 256 * 89250 * 2 + P * 20)        # SURVEY 8(d), bf16: pooled output + unique feature bytes + rois
+    out["roi_pool_fpn"] = {"ms": ms, "rois_per_s": N * P / (ms / 1e3), "algorithmic_bytes": alg, "hbm_gbs": alg / (ms / 1e3) / 1e9,
+                           "frac_of_measured_hbm": alg / (ms / 1e3) / 1e9 / peak_hbm, "boxes": "COCO-shaped (log-uniform 8..600 px)"}
+    # --- RPN post-processing (a5-a8): select top-1000 of 268 569 anchors per image, decode, NMS 0.7, merge
+    lv = []
+    for (h, w) in sizes + [(13, 21)]:
+        n = h * w * 3
+        lg = torch.randn((N, n), generator=g, device=dev)
+        dl = torch.randn((N, n, 4), generator=g, device=dev) * 0.3
+        lv.append(ops.rpn_level_dense(lg, dl, h, w, 3))
+    isz = torch.tensor([[800, 1333]] * N, dtype=torch.int32, device=dev)
+    ms = timed(lambda: ops.rpn_proposals(lv, isz, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0)))
+    alg = N * (268569 * 4 + 4819 * 16 + 4819 * 28)                  # logits + selected deltas + NMS candidates
+    out["rpn_proposals"] = {"ms": ms, "images_per_s": N / (ms / 1e3), "algorithmic_bytes": alg, "hbm_gbs": alg / (ms / 1e3) / 1e9,
+                            "note": "7 launches, latency-bound at this size (5.4 MB per batch)"}
+    # --- box-head post-processing (a13/a14): softmax + decode + per-class NMS + top-100 over 8 x 1000 RoIs x 80 classes
+    logits = torch.randn((N * P, 81), generator=g, device=dev) * 2
+    deltas = torch.randn((N * P, 320), generator=g, device=dev) * 0.5
+    props = rois[:, 1:].contiguous()
+    rimg = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(P)
+    ms = timed(lambda: ops.detections(logits, deltas, props, rimg, isz, isz, 80, max_rois_per_image=P))
+    alg = N * (P * 81 * 4 + P * 320 * 4 + P * 16)
+    out["detections"] = {"ms": ms, "images_per_s": N / (ms / 1e3), "algorithmic_bytes": alg, "hbm_gbs": alg / (ms / 1e3) / 1e9,
+                         "note": "4 launches, latency-bound (13 MB per batch)"}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Python and cannot travel to
     the GPU box (no /root/reference there), so this times the oracle port (oracle/model.py) on all host threads."""
@@ -423,6 +485,10 @@ def main():
                 extras["box_corrector"] = corrector_section(dev)
             except Exception as e:  # noqa: BLE001
                 extras["box_corrector"] = {"error": repr(e)}
+            try:
+                extras["ops"] = ops_section(dev)
+            except Exception as e:  # noqa: BLE001
+                extras["ops"] = {"error": repr(e)}
 
     if rank == 0:
         imgs = world * BATCH * K

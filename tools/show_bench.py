@@ -12,6 +12,9 @@ if "knn" in d:
         print("knn cpu:", d["knn"]["cpu_baseline"])
 if "box_corrector" in d:
     print("corrector:", d["box_corrector"])
+if "ops" in d:
+    for k, v in d["ops"].items():
+        print("op", k, v)
 if "cpu_baseline" in d:
     print("cpu:", d["cpu_baseline"])
 print("clocks:", d.get("clocks"), " launches:", d.get("gpu_launches"))
