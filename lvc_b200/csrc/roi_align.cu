@@ -202,7 +202,7 @@ __device__ __noinline__ void roi_bin_generic(const TI* base, const lvcb200_fmap&
 }
 
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t R, int P, int sampling_ratio,
                     int canon_size, int canon_level, int min_level, TO* __restrict__ out, int out_layout,
                     int64_t out_pitch, int64_t* __restrict__ levels_out) {
@@ -264,25 +264,27 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
           const float x_first = g.start_w + pw * g.bin_w;
           const int xbase = make_tap1(x_first + .5f * xstep, W).lo;
           const int nx = make_tap1(x_first + ((float)(gw - 1) + .5f) * xstep, W).hi - xbase + 1;
-          for (int ry = 0; ry < ny; ry++) {
-            const float wy = sWy[wib][ry];
-            if (wy == 0.f) continue;
-            const TI* rowp = base + ((int64_t)(ybase + ry) * fm.row_stride + xbase) * fm.c_stride + c0;
-            for (int rx0 = 0; rx0 < nx; rx0 += 8) {        // 8 independent 16-byte loads in flight per lane
-              uint4 raw[8];
+          // the ny x nx footprint of the bin, flattened, LB independent 16-byte loads in flight per lane
+          const TI* binp = base + ((int64_t)ybase * fm.row_stride + xbase) * fm.c_stride + c0;
+          const int total = ny * nx;
+          int ry = 0, rx = 0;
+          constexpr int LB = 8;    // loads in flight per lane
+          for (int i0 = 0; i0 < total; i0 += LB) {
+            uint4 raw[LB];
+            float w[LB];
 #pragma unroll
-              for (int u = 0; u < 8; u++) {
-                const int rx = (rx0 + u < nx) ? rx0 + u : nx - 1;   // clamp: a duplicate load, weight forced to 0 below
-                raw[u] = Vec<TI>::load_raw(rowp + (int64_t)rx * fm.c_stride);
-              }
+            for (int u = 0; u < LB; u++) {
+              const bool ok = i0 + u < total;
+              w[u] = ok ? sWy[wib][ry] * sWx[wib][pw][rx] : 0.f;
+              raw[u] = Vec<TI>::load_raw(binp + ((int64_t)ry * fm.row_stride + rx) * fm.c_stride);   // past the end: re-reads the last pixel, weight 0
+              if (ok && (i0 + u + 1 < total)) { if (++rx == nx) { rx = 0; ry++; } }
+            }
 #pragma unroll
-              for (int u = 0; u < 8; u++) {
-                const float w = (rx0 + u < nx) ? wy * sWx[wib][pw][rx0 + u] : 0.f;
-                float v[V];
-                Vec<TI>::unpack(raw[u], v);
+            for (int u = 0; u < LB; u++) {
+              float v[V];
+              Vec<TI>::unpack(raw[u], v);
 #pragma unroll
-                for (int i = 0; i < V; i++) acc[i] += w * v[i];
-              }
+              for (int i = 0; i < V; i++) acc[i] += w[u] * v[i];
             }
           }
         } else {
