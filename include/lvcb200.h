@@ -213,6 +213,24 @@ typedef struct {
 
 int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d /*host*/, void* stream);
 
+/* Layer chain: ONE persistent launch runs n dependent bf16 -> bf16 layers (a ResNet stage, resnet.py:708-731: every
+ * BottleneckBlock.forward :195-211 of the stage) with tile-granular dependencies instead of kernel boundaries.  Layer i may read
+ * (as A or residual) the D buffer of any earlier layer of the chain -- matched by base pointer, same leading dimension --
+ * or buffers written before the launch; it may not overwrite a buffer an earlier layer of the chain touches.  Each layer is
+ * the lvcb200_gemm_bf16 contract restricted to bf16 operands / outputs with N % 64 == 0 and K % 64 == 0, and produces
+ * bit-identical results.  lvcb200_gemm_chain_plan is synchronous (encodes the tensor maps, uploads the layer table into the
+ * caller's device workspace of lvcb200_gemm_chain_workspace() bytes, 256-byte aligned); lvcb200_gemm_chain_run only enqueues
+ * a counter memset and the launch on `stream` (CUDA-graph capturable) and can be repeated while the buffers stay in place. */
+typedef struct {
+  void* workspace;                              /* device: completion counters | layer table */
+  int64_t counter_bytes; int64_t total_tiles;
+  int n_layers; int grid;
+} lvcb200_chain_plan;
+size_t lvcb200_gemm_chain_workspace(const lvcb200_gemm_desc* descs /*host*/, int n);
+int lvcb200_gemm_chain_plan(const lvcb200_gemm_desc* descs /*host*/, int n, void* workspace, size_t workspace_bytes,
+                            lvcb200_chain_plan* plan /*host, out*/);
+int lvcb200_gemm_chain_run(const lvcb200_chain_plan* plan /*host*/, void* stream);
+
 /* Small memory-bound helpers of the conv engine. */
 /* Preprocess + 4x4 space-to-depth.  Replaces GeneralizedRCNN.preprocess_image (lvc/modeling/meta_arch/rcnn.py:324-333:
  * (x - mean) / std, zero pad to /32) and prepares the 7x7/2 stem conv (resnet.py:588-590) as a 3x3 shift-GEMM:

@@ -44,6 +44,10 @@ class GemmDesc(Structure):
                 ("relu", c_int), ("plane_h", c_int), ("plane_w", c_int)]
 
 
+class ChainPlan(Structure):
+    _fields_ = [("workspace", c_void_p), ("counter_bytes", c_int64), ("total_tiles", c_int64), ("n_layers", c_int), ("grid", c_int)]
+
+
 _SIGS = {
     "lvcb200_abi_version": (c_int, []),
     "lvcb200_last_error": (c_char_p, []),
@@ -73,6 +77,9 @@ _SIGS = {
     "lvcb200_knn_verify_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lvcb200_gemm_bf16": (c_int, [POINTER(GemmDesc), c_void_p]),
+    "lvcb200_gemm_chain_workspace": (c_size_t, [POINTER(GemmDesc), c_int]),
+    "lvcb200_gemm_chain_plan": (c_int, [POINTER(GemmDesc), c_int, c_void_p, c_size_t, POINTER(ChainPlan)]),
+    "lvcb200_gemm_chain_run": (c_int, [POINTER(ChainPlan), c_void_p]),
     "lvcb200_stem_s2d4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_maxpool_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_crops_qe": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

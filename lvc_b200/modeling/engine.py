@@ -11,6 +11,7 @@ capture of the whole sequence.  Weights come from a state dict with the referenc
 (batch_norm.py:45-65) is folded into the conv weights / bias in fp32 before the bf16 cast.
 """
 import ctypes
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -125,6 +126,7 @@ class DetectorEngine:
         self.pred_w, self.pred_b = wp.to(dev, torch.bfloat16), bp.to(dev)
         self.mean = torch.tensor(cfg.pixel_mean, dtype=torch.float32, device=dev)
         self.inv_std = (1.0 / torch.tensor(cfg.pixel_std, dtype=torch.float32)).to(dev)
+        self.use_chain = os.environ.get("LVCB200_CHAIN", "1") != "0"   # res stages as layer-chain launches
         self._bufs = {}
         self._graphs = {}
         self.debug = None  # set to a dict to capture intermediates (tests)
@@ -177,15 +179,21 @@ class DetectorEngine:
         if self.debug is not None:
             self.debug["stem_pool"] = x
         feats = {}
-        for i, blk in enumerate(self.blocks):
-            tag = f"b{i}"
-            xin = self._subsample(tag + "_sub", x) if blk["stride"] == 2 else x
-            o1 = self._conv(tag + "_c1", xin, blk["conv1"])
-            o2 = self._conv(tag + "_c2", o1, blk["conv2"])
-            sc = self._conv(tag + "_sc", xin, blk["shortcut"]) if blk["shortcut"] is not None else x
-            x = self._conv(tag + "_c3", o2, blk["conv3"], residual=sc)
-            if blk["last"]:
-                feats[blk["stage"]] = x
+        i = 0
+        while i < len(self.blocks):
+            # one res stage = ONE layer-chain launch (tile-granular dependencies between its 10-70 GEMMs, gemm_chain.cu); the
+            # stride-2 subsample feeding the stage's first block runs before it as its own kernel
+            stage = self.blocks[i]["stage"]
+            with ops.gemm_chain(self.use_chain):
+                while i < len(self.blocks) and self.blocks[i]["stage"] == stage:
+                    blk, tag = self.blocks[i], f"b{i}"
+                    xin = self._subsample(tag + "_sub", x) if blk["stride"] == 2 else x
+                    o1 = self._conv(tag + "_c1", xin, blk["conv1"])
+                    o2 = self._conv(tag + "_c2", o1, blk["conv2"])
+                    sc = self._conv(tag + "_sc", xin, blk["shortcut"]) if blk["shortcut"] is not None else x
+                    x = self._conv(tag + "_c3", o2, blk["conv3"], residual=sc)
+                    i += 1
+            feats[stage] = x
         return feats
 
     def fpn(self, feats):

@@ -6,19 +6,101 @@ import math
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, OUT_NCHW, OUT_NHWC, DetParams, FMap, GemmDesc, RpnLevel, RpnParams
+from ._lib import BF16, F32, OUT_NCHW, OUT_NHWC, ChainPlan, DetParams, FMap, GemmDesc, RpnLevel, RpnParams
 
 _ws = {}
 GEMM_EVENTS = None   # bench.py sets this to a list to time every GEMM launch with CUDA events on the launch stream
 GEMM_RECORD = None   # bench.py sets this to a list to record every GEMM descriptor of a step (replayed alone inside a CUDA graph)
 
 
+GEMM_CHAIN = None    # inside `with gemm_chain():` gemm() calls are collected here and issued as ONE layer-chain launch
+
+
+class gemm_chain:
+    """Context manager: every `gemm()` issued inside is recorded instead of launched; on exit the recorded layers run as one
+    persistent launch with tile-granular dependencies (lvcb200_gemm_chain_*).  Plans (tensor maps + layer table in a device
+    workspace) are cached per exact descriptor list, so steady-state calls -- and CUDA-graph capture -- only enqueue the run.
+    Layers the chain kernel does not take (fp32 heads, N or K not a multiple of 64) make it fall back to per-layer launches."""
+    _plans = {}
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global GEMM_CHAIN
+        if self.enabled:
+            assert GEMM_CHAIN is None, "gemm_chain contexts do not nest"
+            GEMM_CHAIN = []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global GEMM_CHAIN
+        if not self.enabled:
+            return False
+        rec, GEMM_CHAIN = GEMM_CHAIN, None
+        if et is None and rec:
+            run_chain(rec)
+        return False
+
+
+def _desc_key(d):
+    return (d.a_dtype, d.A, d.lda, d.M_rows, d.W, d.ldw, d.bias, d.residual, d.ldr, d.D, d.ldd, d.d_dtype, d.M, d.N, d.K, d.taps,
+            tuple(d.shift), d.relu, d.plane_h, d.plane_w)
+
+
+def chain_eligible(d):
+    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0
+
+
+def run_chain(rec, record=True):
+    """rec: list of (GemmDesc, keepalive tensors).  One lvcb200_gemm_chain_run (plan cached), or per-layer launches."""
+    lib = _lib.load()
+    if len(rec) < 2 or not all(chain_eligible(d) for d, _ in rec):
+        if record and GEMM_RECORD is not None:
+            GEMM_RECORD.extend(rec)
+        replay_gemms(rec)
+        return
+    if record and GEMM_RECORD is not None:
+        GEMM_RECORD.append((rec, "chain"))
+    key = tuple(_desc_key(d) for d, _ in rec)
+    ent = gemm_chain._plans.get(key)
+    if ent is None:
+        import torch
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.LvcB200Error("gemm_chain: plan must be built before CUDA-graph capture (run the step once eagerly)")
+        n = len(rec)
+        arr = (GemmDesc * n)(*[d for d, _ in rec])
+        nbytes = lib.lvcb200_gemm_chain_workspace(arr, n)
+        if nbytes == 0:
+            _lib.check(-1, "lvcb200_gemm_chain_workspace")
+        dev = rec[0][1][0].device
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        plan = ChainPlan()
+        torch.cuda.current_stream().synchronize()
+        _lib.check(lib.lvcb200_gemm_chain_plan(arr, n, _lib.ptr(ws), ws.numel(), ctypes.byref(plan)), "lvcb200_gemm_chain_plan")
+        ent = (plan, ws, [t for _, t in rec])       # keep the workspace and every operand alive with the plan
+        gemm_chain._plans[key] = ent
+    _lib.check(lib.lvcb200_gemm_chain_run(ctypes.byref(ent[0]), _lib.stream_ptr()), "lvcb200_gemm_chain_run")
+
+
 def replay_gemms(descs):
-    """Re-issue recorded GEMM launches (same buffers) on the current stream; used to time the dense layers back to back."""
+    """Re-issue recorded dense launches (same buffers) on the current stream; used to time the dense layers back to back.
+    Entries are (GemmDesc, tensors) for a single launch or (list of those, "chain") for a layer-chain launch."""
     lib = _lib.load()
     sp = _lib.stream_ptr()
-    for d, _ in descs:
-        _lib.check(lib.lvcb200_gemm_bf16(ctypes.byref(d), sp), "lvcb200_gemm_bf16")
+    for d, tag in descs:
+        if isinstance(d, list):
+            run_chain(d, record=False)
+        else:
+            _lib.check(lib.lvcb200_gemm_bf16(ctypes.byref(d), sp), "lvcb200_gemm_bf16")
+
+
+def flatten_recorded(descs):
+    """All per-layer descriptors of a recorded launch list (chains expanded)."""
+    out = []
+    for d, tag in descs:
+        out += [x for x, _ in d] if isinstance(d, list) else [d]
+    return out
 
 
 def _workspace(tag, nbytes, device):
@@ -275,6 +357,9 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
         d.shift[i] = int(s)
     d.relu = int(relu)
     d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
+    if GEMM_CHAIN is not None:
+        GEMM_CHAIN.append((d, (A, W, bias, residual, out)))
+        return out
     if GEMM_RECORD is not None:
         GEMM_RECORD.append((d, (A, W, bias, residual, out)))   # keep the tensors alive with the descriptor
     if GEMM_EVENTS is not None:

@@ -114,3 +114,57 @@ def test_gemm_tf32_operands_f16_out(M, N, K):
     assert bool(((out.float() - ref).abs() <= bound).all()), float(((out.float() - ref).abs() / bound).max())
     # and it is genuinely more accurate than bf16 operands would be (typical error ~ 2^-11 / sqrt(K) scale)
     assert float((out.float() - ref).abs().mean()) < 2e-3 * float(ref.abs().mean())
+
+
+def _bottleneck_stage(n, H, W, cin, bott, cout, nblocks, seed, chain):
+    """A res stage as the engine issues it (resnet.py:195-211): per block 1x1 -> 3x3 -> 1x1 + residual (+ 1x1 shortcut conv on the
+    first block), all on zero-bordered planes.  Returns every layer output (bf16)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    PH, PW = H + 2, W + 2
+    x = ops.Plane.from_nchw(torch.randn(n, cin, H, W, generator=g).bfloat16().to(DEV)).t.view(-1, cin)
+    sh = [(kh - 1) * PW + (kw - 1) for kh in range(3) for kw in range(3)]
+
+    def wt(o, i):
+        return (torch.randn(o, i, generator=g) / i ** 0.5).bfloat16().to(DEV), (torch.randn(o, generator=g) * 0.1).to(DEV)
+
+    params = []
+    for b in range(nblocks):
+        ci = cin if b == 0 else cout
+        params.append(dict(c1=wt(bott, ci), c2=wt(bott, 9 * bott), c3=wt(cout, bott), sc=wt(cout, ci) if b == 0 else None))
+    outs = []
+    with ops.gemm_chain(chain):
+        for p in params:
+            o1 = ops.gemm(x, p["c1"][0], bias=p["c1"][1], relu=True, plane_hw=(PH, PW))
+            o2 = ops.gemm(o1, p["c2"][0], bias=p["c2"][1], relu=True, taps=9, shifts=sh, K=bott, plane_hw=(PH, PW))
+            sc = ops.gemm(x, p["sc"][0], bias=p["sc"][1], plane_hw=(PH, PW)) if p["sc"] is not None else x
+            x = ops.gemm(o2, p["c3"][0], bias=p["c3"][1], residual=sc, relu=True, plane_hw=(PH, PW))
+            outs += [o1, o2, x] + ([sc] if p["sc"] is not None else [])
+    torch.cuda.synchronize()
+    return outs
+
+
+@pytest.mark.parametrize("n,H,W,cin,bott,cout,nblocks", [(2, 25, 42, 256, 64, 256, 3),      # res2-like (BLOCK_N 64 / 256)
+                                                         (2, 30, 44, 256, 128, 512, 4),     # res3-like (BLOCK_N 128 / 256)
+                                                         (3, 50, 84, 512, 256, 1024, 5),    # res4-like, > 148 tiles per layer
+                                                         (1, 13, 21, 1024, 512, 2048, 3),   # res5-like, fewer tiles than SMs
+                                                         (2, 9, 11, 64, 64, 192, 2)])       # tiny, partial N tile (192 of 256)
+def test_layer_chain_matches_per_layer_launches(n, H, W, cin, bott, cout, nblocks):
+    """gemm_chain.cu: one persistent launch with tile-granular dependencies == the same layers launched one by one, bit for bit
+    (identical MMA order per tile), and both within bf16 rounding of the fp32 reference (checked by the tests above)."""
+    want = _bottleneck_stage(n, H, W, cin, bott, cout, nblocks, 11, chain=False)
+    for rep in range(3):                                   # repeated runs reuse the cached plan (counters reset by the run)
+        got = _bottleneck_stage(n, H, W, cin, bott, cout, nblocks, 11, chain=True)
+        assert len(got) == len(want)
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert torch.equal(a, b), f"layer output {i} differs (rep {rep}): max |d| {float((a.float() - b.float()).abs().max())}"
+
+
+def test_layer_chain_rejects_in_chain_overwrite():
+    from lvc_b200 import _lib
+    a = torch.zeros(256, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(64, 64, dtype=torch.bfloat16, device=DEV)
+    b = torch.zeros(256, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.LvcB200Error):
+        with ops.gemm_chain():
+            ops.gemm(a, w, out=b)
+            ops.gemm(b, w, out=a)        # overwrites a buffer layer 0 reads
