@@ -126,7 +126,10 @@ class DetectorEngine:
         self.pred_w, self.pred_b = wp.to(dev, torch.bfloat16), bp.to(dev)
         self.mean = torch.tensor(cfg.pixel_mean, dtype=torch.float32, device=dev)
         self.inv_std = (1.0 / torch.tensor(cfg.pixel_std, dtype=torch.float32)).to(dev)
-        self.use_chain = os.environ.get("LVCB200_CHAIN", "1") != "0"   # res stages as layer-chain launches
+        # res stages run as layer-chain launches (gemm_chain.cu).  res2 stays on per-layer launches: its N = 64 layers issue one tiny
+        # MMA group per 24 KB operand block, which the leaner single-layer producer loop feeds faster (profiles/r01_gemm_layers_*.md)
+        self.use_chain = os.environ.get("LVCB200_CHAIN", "1") != "0"
+        self.chain_stages = tuple(int(x) for x in os.environ.get("LVCB200_CHAIN_STAGES", "3,4,5").split(",") if x)
         self._bufs = {}
         self._graphs = {}
         self.debug = None  # set to a dict to capture intermediates (tests)
@@ -184,7 +187,7 @@ class DetectorEngine:
             # one res stage = ONE layer-chain launch (tile-granular dependencies between its 10-70 GEMMs, gemm_chain.cu); the
             # stride-2 subsample feeding the stage's first block runs before it as its own kernel
             stage = self.blocks[i]["stage"]
-            with ops.gemm_chain(self.use_chain):
+            with ops.gemm_chain(self.use_chain and stage in self.chain_stages):
                 while i < len(self.blocks) and self.blocks[i]["stage"] == stage:
                     blk, tag = self.blocks[i], f"b{i}"
                     xin = self._subsample(tag + "_sub", x) if blk["stride"] == 2 else x
