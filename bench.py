@@ -436,7 +436,8 @@ def main():
         eng.run(dev_images)
         torch.cuda.synchronize()
         recorded, ops.GEMM_RECORD = ops.GEMM_RECORD, None
-        n_gemm = len(recorded)
+        n_gemm = len(recorded)                                   # dense LAUNCHES of the step (a res-stage chain is one)
+        n_layers = len(ops.flatten_recorded(recorded))           # dense layers they cover
         gg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gg):
             ops.replay_gemms(recorded)
@@ -460,19 +461,26 @@ def main():
                     f.write(f"M={M_} N={N_} K={K_} ms={t_:.4f} TFLOPs(padded)={2 * M_ * N_ * K_ / t_ / 1e9:.1f}\n")
             ops.GEMM_EVENTS = None
         eng.use_cuda_graph = use_graph
-        traffic = None   # DRAM bytes per GEMM launch from the committed ncu capture of the same step (profiles/)
-        tp = os.path.join(ROOT, "profiles", "r01_gemm_step_metrics.json")
+        traffic = None   # DRAM bytes per dense launch from the committed ncu capture of the same step (profiles/)
+        tname = "r01_gemm_step_metrics_chain.json" if eng.use_chain else "r01_gemm_step_metrics.json"
+        tp = os.path.join(ROOT, "profiles", tname)
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         alg_tflop = algorithmic_gflop_per_image(cfg) * BATCH / 1e3
         ach = alg_tflop / (gemm_ms / 1e3)
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all dense layers: 104 backbone convs, FPN, RPN head, box head)",
+        roof = {"bound": "tensor",
+                "kernel": "gemm_chain_kernel (res3-res5: one persistent layer-chain launch per stage) + gemm_bf16_tc_kernel (stem, res2, FPN, "
+                          "RPN head, box head): all dense layers of the step" if eng.use_chain else
+                          "gemm_bf16_tc_kernel (all dense layers: 104 backbone convs, FPN, RPN head, box head)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                "traffic_note": "mean dram__bytes_read+write per GEMM launch over the 125 launches of one step (ncu, profiles/r01_gemm_step_metrics.json)",
-                "peak_source": f"{which} (sustained bf16, MEASURED_PEAKS.json)", "launches": n_gemm,
-                "timing": "the step's GEMM launches replayed back to back in a CUDA graph, CUDA events, mean of K replays",
+                "traffic_note": f"mean dram__bytes_read+write per dense launch over the {n_gemm} launches of one step (ncu, profiles/{tname})",
+                "peak_source": f"{which} (sustained bf16, MEASURED_PEAKS.json; itself measured at the 1000 W power cap, ~1.3 GHz)",
+                "launches": n_gemm, "layers": n_layers,
+                "timing": "the step's dense launches replayed back to back in a CUDA graph, CUDA events, mean of K replays",
                 "avg_launch_ms": gemm_ms / max(n_gemm, 1), "gemm_ms_per_step": gemm_ms, "algorithmic_tflop_per_step": alg_tflop,
-                "gemm_share_of_step": gemm_ms / (ms / K)}
+                "gemm_share_of_step": gemm_ms / (ms / K),
+                "power_note": "the dense stack runs at the board power cap (tools/power_probe.py: ~985 W, SM clock 1.6 GHz when sustained); "
+                              "burst replays after idle are ~8 % faster than the sustained figure"}
 
     extras = {}
     if not args.no_extras:   # secondary workloads (BASELINE configs #4, #5); a failure here must not lose the headline line
