@@ -172,6 +172,7 @@ __device__ __forceinline__ Tap1 make_tap1(float y, int size) {
 }
 
 constexpr int kMaxSepGrid = 32;
+constexpr int kPoolTbl = 128;   // (offset, weight) table entries per warp
 
 // Bilinear weights are separable (w(y,x) = wy(y) * wx(x)) and the sample grid of a bin is a product grid, so
 //   sum_{iy,ix} sum_{corners} w * f  ==  sum_{rows} sum_{cols} Wy[row] * Wx[col] * f[row, col]
@@ -209,6 +210,7 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
   constexpr int V = Vec<TI>::N;
   constexpr int MAXP = 8, WS = kMaxSepGrid + 4;
   __shared__ float sWy[8][WS], sWx[8][MAXP][WS];
+  __shared__ int2 sTbl[8][kPoolTbl];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -254,7 +256,9 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
       }
       __syncwarp();
     }
-    for (int c0 = lane * V; c0 < C; c0 += 32 * V) {
+    for (int cb = 0; cb < C; cb += 32 * V) {
+      const int c0 = cb + lane * V;
+      const bool act = c0 < C;              // all lanes stay in the loop (table building and __syncwarp are warp-wide)
       for (int pw = 0; pw < P; pw++) {
         const int bin = ph * P + pw;
         float acc[V];
@@ -264,32 +268,48 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
           const float x_first = g.start_w + pw * g.bin_w;
           const int xbase = make_tap1(x_first + .5f * xstep, W).lo;
           const int nx = make_tap1(x_first + ((float)(gw - 1) + .5f) * xstep, W).hi - xbase + 1;
-          // the ny x nx footprint of the bin, flattened, LB independent 16-byte loads in flight per lane
+          // the ny x nx footprint of the bin, flattened: the lanes first build a table of (element offset, weight) per footprint
+          // pixel in shared memory (one entry per lane per pass), then every lane walks it with LB independent 16-byte loads in
+          // flight -- one LDS.64 + one address add per load.  (Tracking (row, col) per load in registers cost ~25 integer /
+          // predicate instructions per load and made this kernel issue-bound: 1 380 instructions per bin, profiles/.)
           const TI* binp = base + ((int64_t)ybase * fm.row_stride + xbase) * fm.c_stride + c0;
           const int total = ny * nx;
-          int ry = 0, rx = 0;
+          const int cs = (int)fm.c_stride, rs = (int)fm.row_stride * cs;
+          const float* wyp = sWy[wib];
+          const float* wxp = sWx[wib][pw];
           constexpr int LB = 8;    // loads in flight per lane
-          for (int i0 = 0; i0 < total; i0 += LB) {
-            uint4 raw[LB];
-            float w[LB];
-#pragma unroll
-            for (int u = 0; u < LB; u++) {
-              const bool ok = i0 + u < total;
-              w[u] = ok ? sWy[wib][ry] * sWx[wib][pw][rx] : 0.f;
-              raw[u] = Vec<TI>::load_raw(binp + ((int64_t)ry * fm.row_stride + rx) * fm.c_stride);   // past the end: re-reads the last pixel, weight 0
-              if (ok && (i0 + u + 1 < total)) { if (++rx == nx) { rx = 0; ry++; } }
+          for (int ch0 = 0; ch0 < total; ch0 += kPoolTbl) {
+            const int n = total - ch0 < kPoolTbl ? total - ch0 : kPoolTbl;
+            const int npad = (n + LB - 1) / LB * LB;
+            __syncwarp();
+            for (int e = lane; e < npad; e += 32) {
+              const int i = ch0 + (e < n ? e : n - 1);      // padding entries re-read the last pixel with weight 0
+              const int ry = i / nx, rx = i - ry * nx;
+              sTbl[wib][e] = make_int2(ry * rs + rx * cs, __float_as_int(e < n ? wyp[ry] * wxp[rx] : 0.f));
             }
+            __syncwarp();
+            for (int i0 = 0; act && i0 < npad; i0 += LB) {
+              uint4 raw[LB];
+              float w[LB];
 #pragma unroll
-            for (int u = 0; u < LB; u++) {
-              float v[V];
-              Vec<TI>::unpack(raw[u], v);
+              for (int u = 0; u < LB; u++) {
+                const int2 t = sTbl[wib][i0 + u];
+                w[u] = __int_as_float(t.y);
+                raw[u] = Vec<TI>::load_raw(binp + t.x);
+              }
 #pragma unroll
-              for (int i = 0; i < V; i++) acc[i] += w[u] * v[i];
+              for (int u = 0; u < LB; u++) {
+                float v[V];
+                Vec<TI>::unpack(raw[u], v);
+#pragma unroll
+                for (int i = 0; i < V; i++) acc[i] += w[u] * v[i];
+              }
             }
           }
-        } else {
+        } else if (act) {
           roi_bin_generic<TI, V>(base, fm, g, gh, gw, ph, pw, c0, acc);
         }
+        if (!act) continue;
 #pragma unroll
         for (int i = 0; i < V; i++) acc[i] = acc[i] * inv_count;
         if (out_layout == LVCB200_OUT_NHWC) {
