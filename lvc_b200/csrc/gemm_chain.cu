@@ -510,15 +510,58 @@ extern "C" int lvcb200_gemm_chain_plan(const lvcb200_gemm_desc* descs, int n, vo
   // tiles through the L2 -> SM fabric -- kept as an experiment, see DESIGN.md.
   static const char* e_ord = getenv("LVCB200_CHAIN_ORDER");
   static const char* e_slack = getenv("LVCB200_CHAIN_SLACK");
-  const bool wavefront = same_m && e_ord && atoi(e_ord) == 1;
+  static const char* e_l2 = getenv("LVCB200_CHAIN_L2_MB");
+  const int order = e_ord ? atoi(e_ord) : 0;
+  const bool wavefront = same_m && order == 1;
   const double slack_rounds = e_slack ? atof(e_slack) : 3.0;
+  const double l2_budget = (e_l2 ? atof(e_l2) : 72.0) * 1e6;
   std::vector<uint32_t> tiles;
   tiles.reserve((size_t)total);
-  if (!wavefront) {
-    for (int i = 0; i < n; i++)
-      for (int m = 0; m < tab[i].w[W_MTILES]; m++)
-        for (int nt = 0; nt < tab[i].w[W_NTILES]; nt++) tiles.push_back(pack_tile(i, m, nt));
-  } else {
+  // cumulative halo (in 128-row blocks) of each layer behind its producers: the skew that keeps a blocked order dependency-safe
+  std::vector<int> lagc(n, 0);
+  int max_lagc = 0;
+  for (int i = 0; i < n; i++) {
+    int l = 0;
+    if (dep_a[i] >= 0) {
+      const int halo = tab[i].w[W_MAX_SHIFT] > 0 ? (tab[i].w[W_MAX_SHIFT] + BLOCK_M - 1) / BLOCK_M + 1 : 0;
+      l = lagc[dep_a[i]] + halo;
+    }
+    if (dep_r[i] >= 0 && lagc[dep_r[i]] > l) l = lagc[dep_r[i]];
+    lagc[i] = l;
+    if (l > max_lagc) max_lagc = l;
+  }
+  // working set of the chain per 128-row block: input + output of the widest layer, twice (a block's input and output tensors are
+  // alive together), in bf16
+  int widest = 0;
+  for (int i = 0; i < n; i++) if (tab[i].w[W_K] + tab[i].w[W_N] > widest) widest = tab[i].w[W_K] + tab[i].w[W_N];
+  const double ws_per_block = (double)BLOCK_M * 2.0 * widest * 2.0;
+  const int mt0 = tab[0].w[W_MTILES];
+  int chunks = same_m ? (int)((ws_per_block * mt0 + l2_budget - 1) / l2_budget) : 1;
+  if (chunks < 1) chunks = 1;
+  if (order == 0 || !same_m || chunks == 1) {
+    if (!wavefront)
+      for (int i = 0; i < n; i++)
+        for (int m = 0; m < tab[i].w[W_MTILES]; m++)
+          for (int nt = 0; nt < tab[i].w[W_NTILES]; nt++) tiles.push_back(pack_tile(i, m, nt));
+  } else if (order == 2) {
+    // LVCB200_CHAIN_ORDER=2, L2-blocked layer order (experiment): the rows are cut into `chunks` bands whose working set fits the L2
+    // budget; band c runs through ALL layers before band c + 1 starts, so every inter-layer read is served by L2, while inside a
+    // (band, layer) the CTAs still stream the same weight tiles together.  Layer i's band boundaries are shifted up by its
+    // cumulative halo lagc[i] so that the rows a 3x3 needs from the band above were produced in this band.  Measured slower: a
+    // (band, layer) segment of 94-217 tiles is about one round of the 148 CTAs, so every segment waits for the full latency of the
+    // previous one (res4 4.35 ms vs 1.87 ms, res3 0.81 vs 0.64 ms at a 72 MB budget; res2 0.91 vs 0.97 ms at 120 MB).
+    const int Mc = (mt0 + chunks - 1) / chunks;
+    const int last = (mt0 - 1 + max_lagc) / Mc;
+    for (int c = 0; c <= last; c++)
+      for (int i = 0; i < n; i++) {
+        int lo = c * Mc - lagc[i], hi = (c + 1) * Mc - lagc[i];
+        if (lo < 0) lo = 0;
+        if (hi > mt0) hi = mt0;
+        for (int m = lo; m < hi; m++)
+          for (int nt = 0; nt < tab[i].w[W_NTILES]; nt++) tiles.push_back(pack_tile(i, m, nt));
+      }
+  }
+  if (wavefront) {
     int per_step = 0;
     for (int i = 0; i < n; i++) per_step += tab[i].w[W_NTILES];
     const int slack = (int)((slack_rounds * sms + per_step - 1) / per_step) + 1;
@@ -534,11 +577,10 @@ extern "C" int lvcb200_gemm_chain_plan(const lvcb200_gemm_desc* descs, int n, vo
       lag[i] = l;
       if (l > max_lag) max_lag = l;
     }
-    const int mt = tab[0].w[W_MTILES];
-    for (int step = 0; step < mt + max_lag; step++)
+    for (int step = 0; step < mt0 + max_lag; step++)
       for (int i = 0; i < n; i++) {
         const int m = step - lag[i];
-        if (m < 0 || m >= mt) continue;
+        if (m < 0 || m >= mt0) continue;
         for (int nt = 0; nt < tab[i].w[W_NTILES]; nt++) tiles.push_back(pack_tile(i, m, nt));
       }
   }
