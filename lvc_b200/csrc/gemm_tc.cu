@@ -33,7 +33,8 @@ struct GemmParams {
   int has_res;                     // residual tile added on the tensor core: D += R_tile * I (identity B operand)
   int num_stages;                  // smem pipeline depth (runtime: deep for big-K layers, shallow + big staging for small-K)
   int phase_cols;                  // MODE 1: output columns staged per TMA-store phase (64 or 128)
-  int debug;                       // experiments only: 1 = issue no MMAs, 2 = issue no TMA loads (results are garbage)
+  int warp_epi;                    // MODE 1: warp-private staging + one TMA store per warp per 64 columns (no CTA-wide barriers)
+  int debug;                       // experiments only, bit mask: 1 = issue no MMAs, 2 = issue no TMA loads, 4 = issue no TMA stores (results are garbage)
 };
 
 // MODE 0: epilogue stores straight from registers (fp32 heads, tiny N).
@@ -123,7 +124,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // the critical path of this single-thread loop (profiles: ~500 cycles per K iteration regardless of tile width)
       uint32_t stage = 0, phase = 0;
       const int n_tiles = p.n_tiles, k_blocks = p.k_blocks, taps = p.taps, k_elems = p.k_elems, Kdim = p.K, Ndim = p.N;
-      const bool has_res = p.has_res != 0, no_tma = p.debug == 2;
+      const bool has_res = p.has_res != 0, no_tma = (p.debug & 2) != 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
         for (int t = 0; t < taps; t++) {
@@ -163,7 +164,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint64_t adesc0 = make_smem_desc_sw128(smem_a0), bdesc0 = make_smem_desc_sw128(smem_b0);
       uint32_t stage = 0, phase = 0, tc = 0;
       const int n_tiles = p.n_tiles, Ndim = p.N;
-      const bool has_res = p.has_res != 0, no_mma = p.debug == 1;
+      const bool has_res = p.has_res != 0, no_mma = (p.debug & 1) != 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tc++) {
         const int n0 = (tile % n_tiles) * BLOCK_N;
         const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
@@ -225,7 +226,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m0 = (tile / p.n_tiles) * BLOCK_M, n0 = (tile % p.n_tiles) * BLOCK_N;
       const uint32_t b = tc & 1u, bph = (tc >> 1) & 1u;
       if constexpr (MODE == 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's bias reads are done
-      for (int j = et; j < BLOCK_N; j += kEpiThreads) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      if (MODE == 0 || !p.warp_epi)
+        for (int j = et; j < BLOCK_N; j += kEpiThreads) s_bias[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
       if constexpr (MODE == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       const long long m = (long long)m0 + q * 32 + lane;
       bool zero_row = false;
@@ -274,6 +276,72 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
         }
+      } else if (p.warp_epi) {
+        // Warp-private epilogue: every warp owns its 32 rows x (BLOCK_N / 2) columns, stages 64 columns at a time in its own 4 KB
+        // swizzled buffer(s) and issues its own [32 x 64] TMA store -- no CTA-wide barrier anywhere, so the eight warps' TMEM
+        // loads, converts and stores overlap freely.  (The shared-phase version below serialised two bar.syncs and a store
+        // hand-off per phase: ~3.3 us per 128 x 256 tile, which bound every K <= 512 layer; profiles/r01_gemm_modes.md.)
+        const int nbuf = p.phase_cols >> 6;             // private buffers per warp: 1 (deep K loops) or 2
+        const uint32_t my_stg = off_staging + (uint32_t)(warp - kEpiWarp0) * (uint32_t)(nbuf * 4096);
+        constexpr int kColsW = BLOCK_N >= 128 ? BLOCK_N / 2 : BLOCK_N;
+        const int cbeg = BLOCK_N >= 128 ? half * kColsW : 0;
+        const bool works = BLOCK_N >= 128 || half == 0;
+        const bool rows_in = (long long)m0 + q * 32 < p.M;
+        bool released = false;
+        if (works) {
+#pragma unroll 1
+          for (int c = cbeg; c < cbeg + kColsW; c += 64) {
+            if (n0 + c >= p.N) break;
+            const uint32_t buf = nbuf == 2 ? (gphase & 1u) : 0u;
+            if (lane == 0) { if (nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            __syncwarp();
+            uint32_t v[64];
+            tmem_ld32(taddr + c, v);
+            tmem_ld32(taddr + c + 32, v + 32);
+            tmem_ld_wait();
+            if (c + 64 >= cbeg + kColsW || n0 + c + 64 >= p.N) {   // last TMEM read of this tile: hand the accumulator back early
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+              released = true;
+            }
+            uint8_t* rowp = smem_al + my_stg + buf * 4096u + lane * 128;
+            const int sw = lane & 7;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (p.bias != nullptr && n0 + c + 8 * j < p.N) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + 8 * j));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + 8 * j + 4));
+              }
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                float a0 = __uint_as_float(v[8 * j + 2 * e]) + bb[2 * e];
+                float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bb[2 * e + 1];
+                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                if (zero_row) { a0 = 0.f; a1 = 0.f; }
+                if (p.d_f16) { __half2 hh = __floats2half2_rn(a0, a1); ho[e] = *reinterpret_cast<__nv_bfloat162*>(&hh); }
+                else ho[e] = __floats2bfloat162_rn(a0, a1);
+              }
+              *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = o;
+            }
+            fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0 && rows_in && !(p.debug & 4)) {
+              tma_store_2d(&tmap_d, smem_base + my_stg + buf * 4096u, n0 + c, m0 + q * 32);   // rows >= M / cols >= N clipped by the TMA unit
+              tma_store_commit();
+            }
+            gphase++;
+          }
+        }
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        continue;
       } else {
         const int r = q * 32 + lane;
         const int sw = r & 7;                           // SWIZZLE_128B: 16-byte chunk index ^= row & 7
@@ -331,7 +399,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
     }
     if constexpr (MODE == 1) {
-      if (et == 0) tma_store_wait_read<0>();          // smem must stay valid until the last stores have read it
+      if (p.warp_epi ? lane == 0 : et == 0) tma_store_wait_read<0>();   // smem must stay valid until the last stores have read it
     }
   }
   tc_fence_before();
@@ -712,6 +780,10 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (!deep && p.num_stages > 4) p.num_stages = 4;
   p.debug = 0;
+  {
+    static const char* e_we = getenv("LVCB200_GEMM_WEPI");
+    p.warp_epi = (mode == 1 && e_we != nullptr && atoi(e_we) != 0 && ((uintptr_t)d->bias % 16) == 0) ? 1 : 0;   // experiment: same speed as the shared-phase epilogue (profiles/r01_gemm_modes.md)
+  }
   {  // tuning overrides for experiments (tools/gemm_sweep.py); not used by the engine
     static const char* e_dbg = getenv("LVCB200_GEMM_DEBUG");
     if (e_dbg) p.debug = atoi(e_dbg);
@@ -729,12 +801,16 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (rc) return rc;
   td = ta; tr = ta;  // placeholders when unused (a valid map must still be passed by value)
   if (mode == 1 && (rc = make_tmap_2d(&td, d->D, d->M, d->N, d->ldd, BLOCK_M))) return rc;
+  CUtensorMap td32 = td;   // [32 x 64] store box of the warp-private epilogue
+  if (mode == 1 && p.warp_epi && (rc = make_tmap_2d(&td32, d->D, d->M, d->N, d->ldd, 32))) return rc;
   if (p.has_res && (rc = make_tmap_2d(&tr, d->residual, d->M, d->N, d->ldr, BLOCK_M))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   {
     static const char* e_2 = getenv("LVCB200_GEMM_2CTA");
     const int two_cta = e_2 ? atoi(e_2) : 0;
-    if (two_cta && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
+    // 1: every eligible layer; 2: only the big 3x3 convs (long K loops, thousands of tiles: the pair handshake is amortised)
+    const bool want2 = two_cta == 1 || (two_cta == 2 && d->taps == 9 && bn == 256 && d->M >= 100000);
+    if (want2 && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
       GemmParams p2 = p;
       p2.m_tiles = (int)((d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
       p2.phase_cols = bn >= 128 ? 128 : 64;
@@ -750,12 +826,13 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
       }
     }
   }
-  if (tf32) return bn == 256 ? launch_gemm<256, 1, 1>(ta, tw, td, tr, p, s) : launch_gemm<128, 1, 1>(ta, tw, td, tr, p, s);
+  const CUtensorMap& tdu = p.warp_epi ? td32 : td;
+  if (tf32) return bn == 256 ? launch_gemm<256, 1, 1>(ta, tw, tdu, tr, p, s) : launch_gemm<128, 1, 1>(ta, tw, tdu, tr, p, s);
   switch (bn) {
-    case 256: return launch_gemm_mode<256>(mode, ta, tw, td, tr, p, s);
-    case 128: return launch_gemm_mode<128>(mode, ta, tw, td, tr, p, s);
-    case 64: return launch_gemm_mode<64>(mode, ta, tw, td, tr, p, s);
-    case 32: return launch_gemm_mode<32>(mode, ta, tw, td, tr, p, s);
-    default: return launch_gemm_mode<16>(mode, ta, tw, td, tr, p, s);
+    case 256: return launch_gemm_mode<256>(mode, ta, tw, tdu, tr, p, s);
+    case 128: return launch_gemm_mode<128>(mode, ta, tw, tdu, tr, p, s);
+    case 64: return launch_gemm_mode<64>(mode, ta, tw, tdu, tr, p, s);
+    case 32: return launch_gemm_mode<32>(mode, ta, tw, tdu, tr, p, s);
+    default: return launch_gemm_mode<16>(mode, ta, tw, tdu, tr, p, s);
   }
 }
