@@ -8,7 +8,7 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblvcb200.so")
+LIB_PATH = os.environ.get("LVCB200_LIB") or os.path.join(_HERE, "liblvcb200.so")   # LVCB200_LIB: A/B another build on the same box
 
 F32, BF16, U8, F16 = 0, 1, 2, 3
 OUT_NCHW, OUT_NHWC = 0, 1
