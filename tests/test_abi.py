@@ -57,3 +57,29 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_gemm_chain_host_validation():
+    """lvcb200_gemm_chain_* validate the layer list on the host before any CUDA call: unsupported layers and in-chain
+    overwrites are refused (workspace size 0 / error code), a well-formed chain gets a workspace size."""
+    lib = _lib.load()
+
+    def desc(A, W, D, N=64, K=64, M=256, res=0):
+        d = _lib.GemmDesc()
+        d.a_dtype, d.d_dtype = _lib.BF16, _lib.BF16
+        d.A, d.lda, d.M_rows, d.W, d.ldw, d.D, d.ldd = A, K, M, W, K, D, N
+        d.residual, d.ldr = (res, N) if res else (None, 0)
+        d.M, d.N, d.K, d.taps = M, N, K, 1
+        return d
+
+    ok = (_lib.GemmDesc * 2)(desc(0x1000, 0x2000, 0x3000), desc(0x3000, 0x2000, 0x4000))
+    assert lib.lvcb200_gemm_chain_workspace(ok, 2) >= 2 * 640 + 2 * 2 * 4
+    bad_n = (_lib.GemmDesc * 1)(desc(0x1000, 0x2000, 0x3000, N=48))
+    assert lib.lvcb200_gemm_chain_workspace(bad_n, 1) == 0 and b"multiples of 64" in lib.lvcb200_last_error()
+    overwrite = (_lib.GemmDesc * 2)(desc(0x1000, 0x2000, 0x3000), desc(0x3000, 0x2000, 0x1000))
+    assert lib.lvcb200_gemm_chain_workspace(overwrite, 2) == 0 and b"overwrite" in lib.lvcb200_last_error()
+    f32 = desc(0x1000, 0x2000, 0x3000)
+    f32.d_dtype = _lib.F32
+    assert lib.lvcb200_gemm_chain_workspace((_lib.GemmDesc * 1)(f32), 1) == 0
+    plan = _lib.ChainPlan()
+    assert lib.lvcb200_gemm_chain_run(ctypes.byref(plan), None) == -1      # empty plan refused
