@@ -300,6 +300,30 @@ def ops_section(dev):
     alg = N * (P * 81 * 4 + P * 320 * 4 + P * 16)
     out["detections"] = {"ms": ms, "images_per_s": N / (ms / 1e3), "algorithmic_bytes": alg, "hbm_gbs": alg / (ms / 1e3) / 1e9,
                          "note": "4 launches, latency-bound (13 MB per batch)"}
+    # --- "next" row f4: training-side ops (RoIAlign backward, fused IoU + Matcher at RPN anchor count)
+    from lvc_b200.layers import ROIAlign
+    from lvc_b200.modeling import Matcher
+    R4, C4, H4, W4 = 4096, 256, 50, 84
+    x4 = torch.zeros((N, C4, H4, W4), device=dev, requires_grad=True)
+    rois4 = torch.from_numpy(np.concatenate([rng.integers(0, N, (R4, 1)).astype(np.float32), coco_like_boxes(rng, R4)], 1)).to(dev)
+    y4 = ROIAlign(7, 1 / 16, 0, aligned=True)(x4, rois4)
+    g4 = torch.randn(y4.shape, generator=g, device=dev)
+
+    def bwd():
+        x4.grad = None
+        y4.backward(g4, retain_graph=True)
+    ms = timed(bwd)
+    alg = R4 * C4 * 49 * 4 + N * C4 * H4 * W4 * 4 + R4 * 20
+    out["roi_align_backward"] = {"ms": ms, "rois_per_s": R4 / (ms / 1e3), "algorithmic_bytes": alg, "hbm_gbs": alg / (ms / 1e3) / 1e9,
+                                 "note": "NCHW fp32 [8,256,50,84], 4096 RoIs, 7x7, sampling_ratio 0; scatter by RED.ADD (includes the autograd call)"}
+    gtb = torch.from_numpy(coco_like_boxes(rng, 20)).to(dev)
+    anc = torch.from_numpy(coco_like_boxes(rng, 268569)).to(dev)
+    mt = Matcher([0.3, 0.7], [0, -1, 1], True)
+    ms = timed(lambda: mt.match_boxes(gtb, anc))
+    alg = 268569 * (16 + 8 + 1) + 20 * 16
+    out["match_boxes"] = {"ms": ms, "anchors_per_s": 268569 / (ms / 1e3), "algorithmic_bytes": alg, "hbm_gbs": alg / (ms / 1e3) / 1e9,
+                          "note": "fused pairwise_iou + Matcher (RPN labels, low-quality matches) for one image: 20 gt x 268 569 anchors; "
+                                  "the reference materialises the 21 MB IoU matrix"}
     return out
 
 

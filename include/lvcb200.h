@@ -256,6 +256,25 @@ int lvcb200_upsample2_add(const void* top, int n, int Ht, int Wt, int C, void* i
 int lvcb200_crops_qe(const void* image, int image_dtype, int H, int W, const int32_t* geom, int n, int S, const float* mean,
                      const float* inv_std, float* out, void* stream);
 
+/* "Next" row: training-side users of the path's operators.
+ * roi_align_backward: autograd backward of detectron2.layers.roi_align (ROIAlign_cuda.cu:141-306 RoIAlignBackwardFeature):
+ *   grad_output [R,C,ph,pw] fp32, rois [R,5] -> grad_input [N,C,H,W] fp32 (zeroed here, then accumulated with RED.ADD).
+ * pairwise_iou: detectron2/structures/boxes.py:315-347; iou [G,P] fp32 row-major, bit-exact with the library's fp32 arithmetic.
+ * match_boxes: Matcher.__call__ + set_low_quality_matches_ (detectron2/modeling/matcher.py:61-126) over `quality` [G,P] when given,
+ *   else over the IoU of gt_boxes [G,4] x boxes [P,4] computed on the fly (the matrix is never materialised).  thresholds = the
+ *   n interior thresholds (the reference adds -inf / +inf), labels = n + 1 values in {-1,0,1}.  matches [P] int64 (first maximum),
+ *   match_labels [P] int8, matched_vals [P] fp32 optional.  workspace (lvcb200_match_boxes_workspace(G) bytes) is only needed with
+ *   allow_low_quality_matches.  G == 0: matches 0, labels[0]. */
+int lvcb200_roi_align_backward_nchw_f32(const float* grad_output, const float* rois, int R, int N, int C, int H, int W, int pooled_h,
+                                        int pooled_w, float spatial_scale, int sampling_ratio, int aligned, float* grad_input,
+                                        void* stream);
+int lvcb200_pairwise_iou(const float* boxes1, int64_t G, const float* boxes2, int64_t P, float* iou, void* stream);
+size_t lvcb200_match_boxes_workspace(int64_t G);
+int lvcb200_match_boxes(const float* gt_boxes, int64_t G, const float* boxes, const float* quality, int64_t P,
+                        const float* thresholds /*host*/, int n_thresholds, const int8_t* labels /*host*/,
+                        int allow_low_quality_matches, int64_t* matches, int8_t* match_labels, float* matched_vals, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -80,6 +80,12 @@ _SIGS = {
     "lvcb200_gemm_chain_workspace": (c_size_t, [POINTER(GemmDesc), c_int]),
     "lvcb200_gemm_chain_plan": (c_int, [POINTER(GemmDesc), c_int, c_void_p, c_size_t, POINTER(ChainPlan)]),
     "lvcb200_gemm_chain_run": (c_int, [POINTER(ChainPlan), c_void_p]),
+    "lvcb200_roi_align_backward_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                                    c_int, c_void_p, c_void_p]),
+    "lvcb200_pairwise_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "lvcb200_match_boxes_workspace": (c_size_t, [c_int64]),
+    "lvcb200_match_boxes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8), c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lvcb200_stem_s2d4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_maxpool_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_crops_qe": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1,5 +1,6 @@
 from .corrector import BoxCorrectorHead
 from .engine import DetectorEngine
+from .matcher import Matcher, pairwise_iou
 from .rcnn import GeneralizedRCNN
 
-__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN"]
+__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN", "Matcher", "pairwise_iou"]

@@ -1,0 +1,66 @@
+"""Drop-in for detectron2/modeling/matcher.py:8-126 (``Matcher``) and detectron2/structures/boxes.py:315-347 (``pairwise_iou``) on
+liblvcb200 -- the label-assignment step of RPN.label_and_sample_anchors (rpn.py:277-326) and ROIHeads.label_and_sample_proposals
+(lvc/modeling/roi_heads/roi_heads.py:173-278).  ``Matcher.match_boxes(gt, boxes)`` is the fused form: IoU and matching in one pass,
+the [G, P] matrix (G x 268 569 for the RPN anchors of one image) is never written."""
+import ctypes
+from typing import List
+
+import torch
+
+from .. import _lib
+from ..ops import _workspace
+
+
+def pairwise_iou(boxes1, boxes2):
+    """boxes1 [G,4], boxes2 [P,4] (tensors or objects with ``.tensor``) -> IoU [G,P] fp32, bit-exact with the reference's arithmetic."""
+    b1 = getattr(boxes1, "tensor", boxes1)
+    b2 = getattr(boxes2, "tensor", boxes2)
+    _lib.require_cuda(b1, b2)
+    b1, b2 = b1.detach().to(torch.float32).contiguous(), b2.detach().to(torch.float32).contiguous()
+    out = torch.zeros((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    if out.numel():
+        _lib.check(_lib.load().lvcb200_pairwise_iou(_lib.ptr(b1), b1.shape[0], _lib.ptr(b2), b2.shape[0], _lib.ptr(out), _lib.stream_ptr()),
+                   "lvcb200_pairwise_iou")
+    return out
+
+
+class Matcher:
+    def __init__(self, thresholds: List[float], labels: List[int], allow_low_quality_matches: bool = False):
+        thresholds = list(thresholds)
+        assert thresholds[0] > 0                                        # matcher.py:46-55 (the +-inf ends are implicit in the C ABI)
+        assert all(lo <= hi for lo, hi in zip(thresholds[:-1], thresholds[1:]))
+        assert all(l in [-1, 0, 1] for l in labels)
+        assert len(labels) == len(thresholds) + 1
+        self.thresholds, self.labels = thresholds, list(labels)
+        self.allow_low_quality_matches = allow_low_quality_matches
+
+    def _run(self, gt, boxes, quality, G, P, dev):
+        lib = _lib.load()
+        matches = torch.zeros(P, dtype=torch.int64, device=dev)
+        labels = torch.full((P,), self.labels[0], dtype=torch.int8, device=dev)
+        if P == 0:
+            return matches, labels
+        thr = (ctypes.c_float * len(self.thresholds))(*self.thresholds)
+        lab = (ctypes.c_int8 * len(self.labels))(*self.labels)
+        ws = _workspace("match", lib.lvcb200_match_boxes_workspace(G), dev)
+        rc = lib.lvcb200_match_boxes(_lib.ptr(gt), G, _lib.ptr(boxes), _lib.ptr(quality), P, thr, len(self.thresholds), lab,
+                                     int(self.allow_low_quality_matches), _lib.ptr(matches), _lib.ptr(labels), None, _lib.ptr(ws),
+                                     ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "lvcb200_match_boxes")
+        return matches, labels
+
+    def __call__(self, match_quality_matrix):
+        """match_quality_matrix [G, P] fp32 (>= 0) -> matches int64 [P], match_labels int8 [P]  (matcher.py:61-100)."""
+        _lib.require_cuda(match_quality_matrix)
+        assert match_quality_matrix.dim() == 2
+        q = match_quality_matrix.detach().to(torch.float32).contiguous()
+        G, P = q.shape
+        return self._run(None, None, q if G > 0 else None, G, P, q.device) if G > 0 else self._run(None, q.new_zeros((max(P, 1), 4)), None, 0, P, q.device)
+
+    def match_boxes(self, gt_boxes, boxes):
+        """Fused pairwise_iou + matching."""
+        g = getattr(gt_boxes, "tensor", gt_boxes)
+        b = getattr(boxes, "tensor", boxes)
+        _lib.require_cuda(g, b)
+        g, b = g.detach().to(torch.float32).contiguous(), b.detach().to(torch.float32).contiguous()
+        return self._run(g if g.shape[0] else None, b, None, g.shape[0], b.shape[0], b.device)

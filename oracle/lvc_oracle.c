@@ -336,3 +336,108 @@ ORC_API void orc_softmax_rows(const float* x, int64_t R, int K, float* out) {
     float fs = (float)s; for (int k = 0; k < K; k++) o[k] = o[k] / fs;
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * "Next" row f4: training-side users of the same operators.
+ *
+ * RoIAlign backward, NCHW fp32.  Follows detectron2/layers/csrc/ROIAlign/ROIAlign_cuda.cu:141-306
+ * (bilinear_interpolate_gradient + RoIAlignBackwardFeature; the CPU twin is ROIAlign_cpu.cpp:220-330), the in-tree
+ * spec of the autograd backward of torchvision.ops.roi_align reached from detectron2/layers/roi_align.py:15.  grad_in
+ * is accumulated in roi / channel / bin / sample order (the reference's CUDA kernel uses atomicAdd: order unspecified).
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_roi_align_backward(const float* grad_out, int N, int C, int H, int W, const float* rois, int R,
+                                    int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
+                                    float* grad_in) {
+  memset(grad_in, 0, sizeof(float) * (size_t)N * C * H * W);
+  for (int n = 0; n < R; n++) {
+    const float* roi = rois + 5 * n;
+    int batch = (int)roi[0];
+    float offset = aligned ? 0.5f : 0.0f;
+    float roi_start_w = roi[1] * spatial_scale - offset, roi_start_h = roi[2] * spatial_scale - offset;
+    float roi_end_w = roi[3] * spatial_scale - offset, roi_end_h = roi[4] * spatial_scale - offset;
+    float roi_width = roi_end_w - roi_start_w, roi_height = roi_end_h - roi_start_h;
+    if (!aligned) {
+      roi_width = roi_width > 1.f ? roi_width : 1.f;
+      roi_height = roi_height > 1.f ? roi_height : 1.f;
+    }
+    float bin_size_h = roi_height / (float)pooled_h, bin_size_w = roi_width / (float)pooled_w;
+    int grid_h = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_height / (float)pooled_h);
+    int grid_w = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(roi_width / (float)pooled_w);
+    float count = (float)(grid_h * grid_w);
+    for (int c = 0; c < C; c++) {
+      float* gin = grad_in + ((size_t)batch * C + c) * H * W;
+      for (int ph = 0; ph < pooled_h; ph++)
+        for (int pw = 0; pw < pooled_w; pw++) {
+          float g = grad_out[(((size_t)n * C + c) * pooled_h + ph) * pooled_w + pw];
+          for (int iy = 0; iy < grid_h; iy++) {
+            float yy = roi_start_h + ph * bin_size_h + ((float)iy + .5f) * bin_size_h / (float)grid_h;
+            for (int ix = 0; ix < grid_w; ix++) {
+              float xx = roi_start_w + pw * bin_size_w + ((float)ix + .5f) * bin_size_w / (float)grid_w;
+              float x = xx, y = yy;
+              if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;   /* weights 0, indices -1 */
+              if (y <= 0) y = 0;
+              if (x <= 0) x = 0;
+              int y_low = (int)y, x_low = (int)x, y_high, x_high;
+              if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else y_high = y_low + 1;
+              if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else x_high = x_low + 1;
+              float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+              float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+              gin[y_low * W + x_low] += g * w1 / count;
+              gin[y_low * W + x_high] += g * w2 / count;
+              gin[y_high * W + x_low] += g * w3 / count;
+              gin[y_high * W + x_high] += g * w4 / count;
+            }
+          }
+        }
+    }
+  }
+}
+
+/* pairwise_iou (detectron2/structures/boxes.py:315-347; Boxes.area :172-181): separately rounded fp32 ops, iou = 0 where the
+ * intersection is empty.  iou is [G, P] row-major (G = boxes1 = ground truth in the matcher's use). */
+static float orc_iou_pair(const float* a, const float* b) {
+  float area1 = (a[2] - a[0]) * (a[3] - a[1]), area2 = (b[2] - b[0]) * (b[3] - b[1]);
+  float w = (a[2] < b[2] ? a[2] : b[2]) - (a[0] > b[0] ? a[0] : b[0]);
+  float h = (a[3] < b[3] ? a[3] : b[3]) - (a[1] > b[1] ? a[1] : b[1]);
+  if (w < 0.f) w = 0.f;
+  if (h < 0.f) h = 0.f;
+  float inter = w * h;
+  return inter > 0.f ? inter / ((area1 + area2) - inter) : 0.f;
+}
+ORC_API void orc_pairwise_iou(const float* boxes1, int64_t G, const float* boxes2, int64_t P, float* iou) {
+  for (int64_t g = 0; g < G; g++)
+    for (int64_t p = 0; p < P; p++) iou[g * P + p] = orc_iou_pair(boxes1 + 4 * g, boxes2 + 4 * p);
+}
+
+/* Matcher.__call__ + set_low_quality_matches_ (detectron2/modeling/matcher.py:61-126) on the pairwise IoU of gt [G,4] and
+ * proposal / anchor boxes [P,4]: matches[p] = argmax_g iou (first maximum), labels by thresholds (n_thr interior thresholds,
+ * n_thr + 1 labels; the reference's list has -inf / +inf added at the ends, :52-54), optional low-quality promotion (every
+ * prediction that attains a gt's maximum IoU, ties included, is labelled 1).  G == 0: matches 0, labels[0] (:76-87). */
+ORC_API void orc_match_boxes(const float* gt, int64_t G, const float* boxes, int64_t P, const float* thresholds, int n_thr,
+                             const int8_t* labels, int allow_low_quality, int64_t* matches, int8_t* match_labels, float* matched_vals) {
+  if (G == 0) {
+    for (int64_t p = 0; p < P; p++) { matches[p] = 0; match_labels[p] = labels[0]; if (matched_vals) matched_vals[p] = 0.f; }
+    return;
+  }
+  for (int64_t p = 0; p < P; p++) {
+    float best = -1.f; int64_t arg = 0;
+    for (int64_t g = 0; g < G; g++) {
+      float v = orc_iou_pair(gt + 4 * g, boxes + 4 * p);
+      if (v > best) { best = v; arg = g; }
+    }
+    matches[p] = arg;
+    if (matched_vals) matched_vals[p] = best;
+    int8_t l = 1;                                   /* new_full(..., 1), then every (low <= v < high) band overwrites */
+    for (int i = 0; i <= n_thr; i++) {
+      float low = i == 0 ? -INFINITY : thresholds[i - 1], high = i == n_thr ? INFINITY : thresholds[i];
+      if (best >= low && best < high) l = labels[i];
+    }
+    match_labels[p] = l;
+  }
+  if (allow_low_quality)
+    for (int64_t g = 0; g < G; g++) {
+      float hi = -1.f;
+      for (int64_t p = 0; p < P; p++) { float v = orc_iou_pair(gt + 4 * g, boxes + 4 * p); if (v > hi) hi = v; }
+      for (int64_t p = 0; p < P; p++) if (orc_iou_pair(gt + 4 * g, boxes + 4 * p) == hi) match_labels[p] = 1;
+    }
+}

@@ -345,8 +345,47 @@ def gold_crops():
     save("crops", **out)
 
 
+def gold_training_ops():
+    """"Next" row f4: backward of detectron2.layers.ROIAlign through autograd (roi_align.py:63-108 -> torchvision roi_align),
+    pairwise_iou (boxes.py:315-347) and Matcher (matcher.py:8-126) with the RPN and ROI-heads settings of Base-RCNN-FPN
+    (IOU_THRESHOLDS [0.3, 0.7] / labels [0, -1, 1] / low-quality matches; [0.5] / [0, 1])."""
+    from detectron2.layers import ROIAlign
+    from detectron2.modeling.matcher import Matcher
+    from detectron2.structures import Boxes, pairwise_iou
+    rng = np.random.default_rng(41)
+    out = {}
+    for tag, (N, C, H, W, R, scale, ratio) in {"p3": (2, 6, 25, 34, 40, 0.125, 0), "p2r2": (1, 4, 40, 56, 30, 0.25, 2)}.items():
+        x = torch.from_numpy(rng.standard_normal((N, C, H, W)).astype(np.float32)).requires_grad_(True)
+        b = coco_like_boxes(rng, R, W=int(W / scale), H=int(H / scale), min_side=4.0, max_side=H / scale)
+        b[0] = [10.0, 10.0, 10.0, 30.0]                                   # zero-width roi
+        b[1] = [-30.0, -20.0, 60.0, 50.0]                                 # hangs over the top-left corner
+        rois = torch.from_numpy(np.concatenate([rng.integers(0, N, (R, 1)).astype(np.float32), b], 1))
+        y = ROIAlign(7, scale, ratio, aligned=True)(x, rois)
+        g = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32))
+        y.backward(g)
+        out.update({f"{tag}_shape": np.array([N, C, H, W]), f"{tag}_rois": rois, f"{tag}_scale": np.float32(scale), f"{tag}_ratio": ratio,
+                    f"{tag}_grad_out": g, f"{tag}_grad_in": x.grad.detach()})
+    gt = coco_like_boxes(rng, 12)
+    gt[5] = gt[4]                                                         # duplicate gt: argmax tie -> first index
+    props = coco_like_boxes(rng, 3000)
+    props[:12] = gt                                                       # exact hits (IoU 1)
+    props[12:24] = gt + rng.uniform(-6, 6, (12, 4)).astype(np.float32)    # near hits
+    props[30] = props[31]                                                 # duplicate proposals: low-quality ties
+    iou = pairwise_iou(Boxes(torch.from_numpy(gt)), Boxes(torch.from_numpy(props)))
+    out.update(gt=gt, props=props, iou=iou)
+    for tag, thr, lab, low in (("rpn", [0.3, 0.7], [0, -1, 1], True), ("roi", [0.5], [0, 1], False)):
+        m, l = Matcher(thr, lab, allow_low_quality_matches=low)(iou)
+        out.update({f"{tag}_thr": np.array(thr, np.float32), f"{tag}_lab": np.array(lab, np.int8), f"{tag}_low": int(low),
+                    f"{tag}_matches": m, f"{tag}_labels": l})
+    m0, l0 = Matcher([0.5], [0, 1])(pairwise_iou(Boxes(torch.zeros(0, 4)), Boxes(torch.from_numpy(props[:5]))))
+    out.update(empty_matches=m0, empty_labels=l0)
+    save("training_ops", **out)
+
+
 def main():
-    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector", "cand", "crops"]
+    which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector", "cand", "crops", "train"]
+    if "train" in which:
+        gold_training_ops()
     if "cand" in which:
         gold_candidates()
     if "crops" in which:

@@ -390,3 +390,36 @@ def get_crops_qe(img, boxes, operation="context", size=224):
                 px = min(int(np.floor(np.float32(ox) * sx)), Wp - 1)
                 out[i, :, oy, ox] = pad[:, py, px]
     return out
+
+
+# ------------------------------------------------------------------------------------ "next" row f4: training-side ops
+def roi_align_backward(grad_out, rois, input_shape, spatial_scale, sampling_ratio, aligned):
+    """autograd backward of detectron2.layers.roi_align (ROIAlign_cuda.cu:141-306): grad_out [R,C,ph,pw] -> grad_in [N,C,H,W]."""
+    g, r = _f32(grad_out), _f32(rois)
+    N, C, H, W = input_shape
+    R, _, ph, pw = g.shape
+    out = np.zeros((N, C, H, W), np.float32)
+    lib().orc_roi_align_backward(_p(g, _f32p), N, C, H, W, _p(r, _f32p), R, ph, pw, ctypes.c_float(spatial_scale),
+                                 int(sampling_ratio), int(bool(aligned)), _p(out, _f32p))
+    return out
+
+
+def pairwise_iou(boxes1, boxes2):
+    """detectron2/structures/boxes.py:315-347 -> [G, P] fp32."""
+    a, b = _f32(boxes1).reshape(-1, 4), _f32(boxes2).reshape(-1, 4)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if out.size:
+        lib().orc_pairwise_iou(_p(a, _f32p), ctypes.c_int64(a.shape[0]), _p(b, _f32p), ctypes.c_int64(b.shape[0]), _p(out, _f32p))
+    return out
+
+
+def match_boxes(gt, boxes, thresholds, labels, allow_low_quality):
+    """Matcher(thresholds, labels, allow_low_quality)(pairwise_iou(gt, boxes)) (matcher.py:61-126) -> matches int64 [P], labels int8 [P]."""
+    a, b = _f32(gt).reshape(-1, 4), _f32(boxes).reshape(-1, 4)
+    P = b.shape[0]
+    m, l, v = np.zeros(P, np.int64), np.zeros(P, np.int8), np.zeros(P, np.float32)
+    th, lb = _f32(thresholds), np.ascontiguousarray(labels, np.int8)
+    lib().orc_match_boxes(_p(a, _f32p), ctypes.c_int64(a.shape[0]), _p(b, _f32p), ctypes.c_int64(P), _p(th, _f32p), len(th),
+                          lb.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), int(bool(allow_low_quality)), _p(m, _i64p),
+                          l.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(v, _f32p))
+    return m, l, v

@@ -302,3 +302,50 @@ def test_knn_vs_oracle_tie_aware():
     r1 = ops.KnnBank(cu(bank[:37]), cu(cls[:37])).verify(cu(q[:5]), cu(qc[:5]), topk=10, knn=5)
     w1 = O.knn_verify(bank[:37], cls[:37], q[:5], qc[:5], topk=10, knn=5)
     assert np.array_equal(r1["top_idx"].cpu().numpy(), w1["top_idx"]) and np.array_equal(r1["keep"].cpu().numpy(), w1["keep"])
+
+
+# ---------------------------------------------------------------- "next" row f4: training-side ops
+def test_roi_align_backward_golden_and_oracle(golden):
+    """autograd backward of lvc_b200.layers.roi_align == the reference's (torchvision) backward; fp32 scatter-add: <= 1e-5 of scale."""
+    from lvc_b200.layers import ROIAlign
+    g = golden("training_ops")
+    for tag in ("p3", "p2r2"):
+        N, C, H, W = (int(v) for v in g[f"{tag}_shape"])
+        x = torch.zeros((N, C, H, W), device=DEV, requires_grad=True)
+        rois = torch.from_numpy(g[f"{tag}_rois"]).to(DEV)
+        y = ROIAlign(7, float(g[f"{tag}_scale"]), int(g[f"{tag}_ratio"]), aligned=True)(x, rois)
+        y.backward(torch.from_numpy(g[f"{tag}_grad_out"]).to(DEV))
+        want = g[f"{tag}_grad_in"]
+        assert np.abs(x.grad.cpu().numpy() - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), tag
+    # larger random case against the C oracle
+    rng = np.random.default_rng(3)
+    N, C, H, W, R = 2, 16, 50, 84, 300
+    rois = np.concatenate([rng.integers(0, N, (R, 1)).astype(np.float32), coco_like_boxes(rng, R)], 1)
+    go = rng.standard_normal((R, C, 7, 7)).astype(np.float32)
+    x = torch.zeros((N, C, H, W), device=DEV, requires_grad=True)
+    ROIAlign(7, 1 / 16, 0, aligned=True)(x, torch.from_numpy(rois).to(DEV)).backward(torch.from_numpy(go).to(DEV))
+    want = O.roi_align_backward(go, rois, (N, C, H, W), 1 / 16, 0, True)
+    assert np.abs(x.grad.cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_pairwise_iou_and_matcher(golden):
+    """bit-exact IoU matrix, matches (first maximum) and labels, on the reference's fixture and on an RPN-sized random case;
+    matrix form (Matcher.__call__) and fused form (match_boxes) agree."""
+    from lvc_b200.modeling import Matcher, pairwise_iou
+    g = golden("training_ops")
+    gt, props = torch.from_numpy(g["gt"]).to(DEV), torch.from_numpy(g["props"]).to(DEV)
+    iou = pairwise_iou(gt, props)
+    assert np.array_equal(iou.cpu().numpy(), g["iou"])
+    for tag in ("rpn", "roi"):
+        mt = Matcher(g[f"{tag}_thr"].tolist(), g[f"{tag}_lab"].tolist(), bool(g[f"{tag}_low"]))
+        for m, l in (mt(iou), mt.match_boxes(gt, props)):
+            assert np.array_equal(m.cpu().numpy(), g[f"{tag}_matches"]) and np.array_equal(l.cpu().numpy(), g[f"{tag}_labels"]), tag
+    m0, l0 = Matcher([0.5], [0, 1])(torch.zeros((0, 5), device=DEV))
+    assert np.array_equal(m0.cpu().numpy(), g["empty_matches"]) and np.array_equal(l0.cpu().numpy(), g["empty_labels"])
+    m0, l0 = Matcher([0.5], [0, 1]).match_boxes(torch.zeros((0, 4), device=DEV), props[:5])
+    assert np.array_equal(m0.cpu().numpy(), g["empty_matches"]) and np.array_equal(l0.cpu().numpy(), g["empty_labels"])
+    rng = np.random.default_rng(9)
+    gtb, anc = coco_like_boxes(rng, 37), coco_like_boxes(rng, 268569)
+    wm, wl, _ = O.match_boxes(gtb, anc, [0.3, 0.7], [0, -1, 1], True)
+    m, l = Matcher([0.3, 0.7], [0, -1, 1], True).match_boxes(torch.from_numpy(gtb).to(DEV), torch.from_numpy(anc).to(DEV))
+    assert np.array_equal(m.cpu().numpy(), wm) and np.array_equal(l.cpu().numpy(), wl)
