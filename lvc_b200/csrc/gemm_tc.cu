@@ -807,13 +807,14 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   {
     static const char* e_2 = getenv("LVCB200_GEMM_2CTA");
-    const int two_cta = e_2 ? atoi(e_2) : 0;
+    const int two_cta = e_2 ? atoi(e_2) : 2;   // default: 2-CTA tiles for the big 3x3 convs only (same-box A/B: dense stack -1.7 % sustained)
     // 1: every eligible layer; 2: only the big 3x3 convs (long K loops, thousands of tiles: the pair handshake is amortised)
     const bool want2 = two_cta == 1 || (two_cta == 2 && d->taps == 9 && bn == 256 && d->M >= 100000);
     if (want2 && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
       GemmParams p2 = p;
       p2.m_tiles = (int)((d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
-      p2.phase_cols = bn >= 128 ? 128 : 64;
+      static const char* e_2p = getenv("LVCB200_GEMM_2CTA_PHASE");
+      p2.phase_cols = e_2p ? atoi(e_2p) : (bn >= 128 ? 128 : 64);
       const int stage_bytes2 = kStageBytesA + (bn / 2) * BLOCK_K * 2;
       p2.num_stages = (232448 - (kCtrlBytes + 1024) - 2 * BLOCK_M * p2.phase_cols * 2 - (p2.has_res ? kIdentBytes / 2 : 0)) / stage_bytes2;
       if (p2.num_stages > kMaxStages) p2.num_stages = kMaxStages;
