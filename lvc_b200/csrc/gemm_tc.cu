@@ -808,8 +808,10 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   {
     static const char* e_2 = getenv("LVCB200_GEMM_2CTA");
     const int two_cta = e_2 ? atoi(e_2) : 2;   // default: 2-CTA tiles for the big 3x3 convs only (same-box A/B: dense stack -1.7 % sustained)
-    // 1: every eligible layer; 2: only the big 3x3 convs (long K loops, thousands of tiles: the pair handshake is amortised)
-    const bool want2 = two_cta == 1 || (two_cta == 2 && d->taps == 9 && bn == 256 && d->M >= 100000);
+    // 1: every eligible layer; 2 (default): long K loops on wide tiles -- the big 3x3 convs and the fc layers (per-shape table in
+    // profiles/r01_gemm_modes.md: the pair handshake is amortised and half the B bytes per SM buy two more ring stages); 3: big 3x3 only
+    const bool want2 = two_cta == 1 || (two_cta == 3 && d->taps == 9 && bn == 256 && d->M >= 100000) ||
+                       (two_cta == 2 && bn == 256 && !p.has_res && k_iters >= 16 && (d->M >= 100000 || (d->taps == 1 && d->M >= 8000)));
     if (want2 && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
       GemmParams p2 = p;
       p2.m_tiles = (int)((d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
