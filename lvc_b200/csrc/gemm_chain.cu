@@ -15,6 +15,8 @@
 // BLOCK_N (8 blocks in flight at BLOCK_N = 64, 4 at 256), residual added on the tensor core (D += R * I with a 16 x 16 identity: four
 // N = 16 MMAs per 64 residual columns), epilogue TMEM -> bias/ReLU/border-zero -> bf16 -> swizzled staging -> TMA store issued by a
 // dedicated store thread, which also publishes the tile's completion counter once its stores have landed.
+// Weight-stationary layers (conv3: 1x1, K <= 256, several N tiles): a CTA's tiles of the layer share one N tile, so its weight tile is
+// loaded once into the top of the operand buffer and only A / residual blocks stream (same-box A/B: dense stack -1.4 % sustained).
 #include <string.h>
 #include <vector>
 
@@ -86,11 +88,11 @@ __device__ __forceinline__ void wait_rows_ready(const uint32_t* cnt, int lo, int
 
 // ring allocation rule shared by the producer and the MMA issuer: block of u units at `pos`, skipping to 0 instead of wrapping
 struct RingPos {
-  uint32_t pos = 0, k = 0;
+  uint32_t pos = 0, k = 0, units = kUnits;   // `units`: ring size; the top of the buffer is lent to a resident weight tile in stationary mode
   __device__ __forceinline__ uint32_t place(uint32_t u, uint32_t& pad) {   // returns the first unit of the block
-    pad = (pos + u > (uint32_t)kUnits) ? (uint32_t)kUnits - pos : 0u;
+    pad = (pos + u > units) ? units - pos : 0u;
     const uint32_t start = pad ? 0u : pos;
-    pos = start + u; if (pos == (uint32_t)kUnits) pos = 0;
+    pos = start + u; if (pos == units) pos = 0;
     return start;
   }
 };
@@ -153,7 +155,7 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
       if (lane < 4) tma_prefetch_desc(reinterpret_cast<const CUtensorMap*>(ly) + lane);
       const int m = (int)(e & 0xfffffu), m0 = m * BLOCK_M;
       const int dep_a_off = __shfl_sync(0xffffffffu, wv, W_DEP_A_OFF), dep_r_off = __shfl_sync(0xffffffffu, wv, W_DEP_R_OFF);
-      const int has_res = __shfl_sync(0xffffffffu, wv, W_HAS_RES);
+      const int has_res = __shfl_sync(0xffffffffu, wv, W_HAS_RES) & 1;
       bool waited = false;
       if (dep_a_off >= 0) {
         const int min_shift = __shfl_sync(0xffffffffu, wv, W_MIN_SHIFT), max_shift = __shfl_sync(0xffffffffu, wv, W_MAX_SHIFT);
@@ -179,6 +181,7 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
     if (lane == 0) {   // ============================================ TMA producer
       RingPos rp;
       uint32_t rel_k = 0, used = 0, lens = 0;             // oldest unreleased block, units held by unreleased blocks, 4-bit lengths
+      int cur_mode = -1;
       for (int i = 0; i < my_tiles; i++) {
         const uint32_t slot = (uint32_t)i % kQueueDepth, use = (uint32_t)i / kQueueDepth;
         mbar_wait(bar_qfull + 8 * slot, use & 1u);
@@ -186,25 +189,46 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
         const uint32_t e = (uint32_t)q[W_TILE];
         const ChainLayer* ly = layers + (e >> 24);
         const int bn = q[W_BN], k_blocks = q[W_KBLOCKS], taps = q[W_TAPS], Kdim = q[W_K], Ndim = q[W_N];
-        const bool has_res = q[W_HAS_RES] != 0;
+        const int hr = q[W_HAS_RES];
+        const bool has_res = (hr & 1) != 0, stat = (hr & 2) != 0;
         int shift[9];
 #pragma unroll
         for (int t = 0; t < 9; t++) shift[t] = q[W_SHIFT0 + t];
         mbar_arrive(bar_qempty + 8 * slot);
         fence_proxy_async_all();               // the scheduler's dependency acquire is ordered before this thread's TMA loads
         const int m0 = (int)(e & 0xfffffu) * BLOCK_M, n0 = (int)((e >> 20) & 15u) * bn;
-        const uint32_t u = 2u + (uint32_t)(bn >> 6);
-        const uint32_t stage_bytes = 16384u + (uint32_t)bn * 128u;
+        // Weight-stationary layers (1x1, K <= 256, BLOCK_N = 256, several N tiles: conv3 of a bottleneck): this CTA's tiles of the layer all
+        // have the same N tile, so its weight tile (K x 256 bf16 <= 128 KB) is loaded ONCE into the top of the operand buffer and the
+        // ring shrinks to the units below it; per tile only A (and the residual) stream through L2 -> SM, which is what paces these
+        // layers (profiles/r01_gemm_timeline.md).  Entering / leaving the mode drains the ring.
+        const int mode = stat ? (int)(e >> 20) : -1;               // (layer, N tile) of a stationary tile
+        bool load_w = false;
+        if (mode != cur_mode) {
+          while (rel_k != rp.k) {                                   // drain: every outstanding block released (so the old weight tile is dead too)
+            mbar_wait(bar_empty + 8 * (rel_k & 7u), (rel_k >> 3) & 1u);
+            used -= (lens >> (4 * (rel_k & 7u))) & 15u;
+            rel_k++;
+          }
+          rp.pos = 0;
+          rp.units = stat ? (uint32_t)(kUnits - 4 * k_blocks) : (uint32_t)kUnits;
+          cur_mode = mode;
+          load_w = stat;
+        }
+        const uint32_t u = stat ? 2u : 2u + (uint32_t)(bn >> 6);
+        const uint32_t u_res = stat ? 4u : u;
+        const uint32_t w_base = smem_base + (uint32_t)(kUnits - 4 * k_blocks) * kUnitBytes;
+        const uint32_t stage_bytes = 16384u + ((stat && !load_w) ? 0u : (uint32_t)bn * 128u);
         const int per = bn >= 128 ? 2 : 1;
         const int n_res = has_res ? (((Ndim - n0 < bn ? Ndim - n0 : bn) / 64 + per - 1) / per) : 0;
         const int n_main = taps * k_blocks;
         const int iters = n_main + n_res;
         int tp = 0, kb = 0;
         for (int it = 0; it < iters; it++) {
+          const uint32_t ub = it < n_main ? u : u_res;
           uint32_t pad;
-          const uint32_t start = rp.place(u, pad);
-          const uint32_t need = pad + u;
-          while (used + need > (uint32_t)kUnits || rp.k - rel_k >= (uint32_t)kRingBars) {   // oldest blocks release their units in order
+          const uint32_t start = rp.place(ub, pad);
+          const uint32_t need = pad + ub;
+          while (used + need > rp.units || rp.k - rel_k >= (uint32_t)kRingBars) {   // oldest blocks release their units in order
             mbar_wait(bar_empty + 8 * (rel_k & 7u), (rel_k >> 3) & 1u);
             used -= (lens >> (4 * (rel_k & 7u))) & 15u;
             rel_k++;
@@ -220,7 +244,8 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
             for (int t = 1; t < 9; t++) sh = tp == t ? shift[t] : sh;
             mbar_arrive_expect_tx(fb, stage_bytes);
             tma_load_2d(dst, &ly->ta, fb, kb * BLOCK_K, m0 + sh);
-            tma_load_2d(dst + 16384, &ly->tw, fb, tp * Kdim + kb * BLOCK_K, n0);
+            if (!stat) tma_load_2d(dst + 16384, &ly->tw, fb, tp * Kdim + kb * BLOCK_K, n0);
+            else if (load_w) tma_load_2d(w_base + (uint32_t)kb * 32768u, &ly->tw, fb, kb * BLOCK_K, n0);
             if (++kb == k_blocks) { kb = 0; tp++; }
           } else {   // residual [128 x 64] tiles as extra A operands, two per block when BLOCK_N >= 128
             const int j = (it - n_main) * per;
@@ -237,16 +262,26 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
       const uint64_t ident_desc = make_smem_desc_sw128(smem_base + kOffIdent);
       constexpr uint32_t idesc_res = make_idesc_bf16(BLOCK_M, 16);
       RingPos rp;
+      int cur_mode = -1;
       for (int i = 0; i < my_tiles; i++) {
         const uint32_t slot = (uint32_t)i % kQueueDepth, use = (uint32_t)i / kQueueDepth;
         mbar_wait(bar_qfull + 8 * slot, use & 1u);
         const volatile int* q = queue + slot * 32;
         const uint32_t e = (uint32_t)q[W_TILE];
-        const int bn = q[W_BN], Ndim = q[W_N], k_iters = q[W_TAPS] * q[W_KBLOCKS];
-        const bool has_res = q[W_HAS_RES] != 0;
+        const int bn = q[W_BN], Ndim = q[W_N], k_blocks = q[W_KBLOCKS], k_iters = q[W_TAPS] * k_blocks;
+        const int hr = q[W_HAS_RES];
+        const bool has_res = (hr & 1) != 0, stat = (hr & 2) != 0;
         mbar_arrive(bar_qempty + 8 * slot);
         const int n0 = (int)((e >> 20) & 15u) * bn;
-        const uint32_t u = 2u + (uint32_t)(bn >> 6);
+        const int mode = stat ? (int)(e >> 20) : -1;
+        if (mode != cur_mode) {                 // same rule as the producer: ring restarts at unit 0 with the new size
+          rp.pos = 0;
+          rp.units = stat ? (uint32_t)(kUnits - 4 * k_blocks) : (uint32_t)kUnits;
+          cur_mode = mode;
+        }
+        const uint32_t u = stat ? 2u : 2u + (uint32_t)(bn >> 6);
+        const uint32_t u_res = stat ? 4u : u;
+        const uint64_t wdesc0 = make_smem_desc_sw128(smem_base + (uint32_t)(kUnits - 4 * k_blocks) * kUnitBytes);
         const uint32_t b = (uint32_t)i & 1u, bph = ((uint32_t)i >> 1) & 1u;
         mbar_wait(bar_tempty + 8 * b, bph ^ 1u);
         tc_fence_after();
@@ -260,7 +295,7 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
           mbar_wait(bar_full + 8 * (rp.k & 7u), (rp.k >> 3) & 1u);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_base + start * kUnitBytes);
-          const uint64_t bdesc = adesc + (16384u >> 4);
+          const uint64_t bdesc = stat ? wdesc0 + (uint64_t)ki * (32768u >> 4) : adesc + (16384u >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++)
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
@@ -272,7 +307,7 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
           for (int j = 0; j < bn / 64 && n0 + j * 64 < Ndim; j += per) {
             const bool two = per == 2 && (n0 + (j + 1) * 64 < Ndim);
             uint32_t pad;
-            const uint32_t start = rp.place(u, pad);
+            const uint32_t start = rp.place(u_res, pad);
             mbar_wait(bar_full + 8 * (rp.k & 7u), (rp.k >> 3) & 1u);
             tc_fence_after();
             const uint64_t adesc = make_smem_desc_sw128(smem_base + start * kUnitBytes);
@@ -480,6 +515,15 @@ extern "C" int lvcb200_gemm_chain_plan(const lvcb200_gemm_desc* descs, int n, vo
     LVC_REQUIRE(L.w[W_MTILES] < (1 << 20) && L.w[W_NTILES] <= 15, "gemm_chain_plan: layer too large for the tile list encoding");
     L.w[W_KBLOCKS] = d->K / BLOCK_K;
     L.w[W_HAS_RES] = d->residual ? 1 : 0;
+    {  // bit 1: weight-stationary (see the producer): 1x1, K <= 256, BLOCK_N = 256, >= 2 N tiles, and every CTA keeps its N tile
+      static const char* e_ws = getenv("LVCB200_CHAIN_WSTAT");
+      static const char* e_ord0 = getenv("LVCB200_CHAIN_ORDER");
+      const int grid0 = (int)(total < sms ? total : sms);
+      const bool layer_order = !(e_ord0 && atoi(e_ord0) != 0);
+      if ((e_ws == nullptr || atoi(e_ws) != 0) && layer_order && d->taps == 1 && bn == 256 && L.w[W_KBLOCKS] <= 4 && L.w[W_NTILES] >= 2 &&
+          grid0 % L.w[W_NTILES] == 0 && d->N % 256 == 0)
+        L.w[W_HAS_RES] |= 2;
+    }
     L.w[W_CNT_OFF] = cnt_off;
     L.w[W_DEP_A_OFF] = -1; L.w[W_DEP_R_OFF] = -1;
     if (L.w[W_MTILES] != tab[0].w[W_MTILES]) same_m = false;
