@@ -210,13 +210,13 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
             rel_k++;
           }
           rp.pos = 0;
-          rp.units = stat ? (uint32_t)(kUnits - 4 * k_blocks) : (uint32_t)kUnits;
+          rp.units = stat ? (uint32_t)(kUnits - taps * k_blocks * (bn >> 6)) : (uint32_t)kUnits;
           cur_mode = mode;
           load_w = stat;
         }
         const uint32_t u = stat ? 2u : 2u + (uint32_t)(bn >> 6);
         const uint32_t u_res = stat ? 4u : u;
-        const uint32_t w_base = smem_base + (uint32_t)(kUnits - 4 * k_blocks) * kUnitBytes;
+        const uint32_t w_base = smem_base + (uint32_t)(kUnits - taps * k_blocks * (bn >> 6)) * kUnitBytes;   // resident weight tile: one [bn x 64] block per K block
         const uint32_t stage_bytes = 16384u + ((stat && !load_w) ? 0u : (uint32_t)bn * 128u);
         const int per = bn >= 128 ? 2 : 1;
         const int n_res = has_res ? (((Ndim - n0 < bn ? Ndim - n0 : bn) / 64 + per - 1) / per) : 0;
@@ -245,7 +245,7 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
             mbar_arrive_expect_tx(fb, stage_bytes);
             tma_load_2d(dst, &ly->ta, fb, kb * BLOCK_K, m0 + sh);
             if (!stat) tma_load_2d(dst + 16384, &ly->tw, fb, tp * Kdim + kb * BLOCK_K, n0);
-            else if (load_w) tma_load_2d(w_base + (uint32_t)kb * 32768u, &ly->tw, fb, kb * BLOCK_K, n0);
+            else if (load_w) tma_load_2d(w_base + (uint32_t)it * ((uint32_t)bn * 128u), &ly->tw, fb, tp * Kdim + kb * BLOCK_K, n0);
             if (++kb == k_blocks) { kb = 0; tp++; }
           } else {   // residual [128 x 64] tiles as extra A operands, two per block when BLOCK_N >= 128
             const int j = (it - n_main) * per;
@@ -276,12 +276,12 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
         const int mode = stat ? (int)(e >> 20) : -1;
         if (mode != cur_mode) {                 // same rule as the producer: ring restarts at unit 0 with the new size
           rp.pos = 0;
-          rp.units = stat ? (uint32_t)(kUnits - 4 * k_blocks) : (uint32_t)kUnits;
+          rp.units = stat ? (uint32_t)(kUnits - k_iters * (bn >> 6)) : (uint32_t)kUnits;
           cur_mode = mode;
         }
         const uint32_t u = stat ? 2u : 2u + (uint32_t)(bn >> 6);
         const uint32_t u_res = stat ? 4u : u;
-        const uint64_t wdesc0 = make_smem_desc_sw128(smem_base + (uint32_t)(kUnits - 4 * k_blocks) * kUnitBytes);
+        const uint64_t wdesc0 = make_smem_desc_sw128(smem_base + (uint32_t)(kUnits - k_iters * (bn >> 6)) * kUnitBytes);
         const uint32_t b = (uint32_t)i & 1u, bph = ((uint32_t)i >> 1) & 1u;
         mbar_wait(bar_tempty + 8 * b, bph ^ 1u);
         tc_fence_after();
@@ -295,7 +295,7 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
           mbar_wait(bar_full + 8 * (rp.k & 7u), (rp.k >> 3) & 1u);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(smem_base + start * kUnitBytes);
-          const uint64_t bdesc = stat ? wdesc0 + (uint64_t)ki * (32768u >> 4) : adesc + (16384u >> 4);
+          const uint64_t bdesc = stat ? wdesc0 + (uint64_t)ki * (uint64_t)((bn * 128) >> 4) : adesc + (16384u >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++)
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
@@ -520,8 +520,10 @@ extern "C" int lvcb200_gemm_chain_plan(const lvcb200_gemm_desc* descs, int n, vo
       static const char* e_ord0 = getenv("LVCB200_CHAIN_ORDER");
       const int grid0 = (int)(total < sms ? total : sms);
       const bool layer_order = !(e_ord0 && atoi(e_ord0) != 0);
-      if ((e_ws == nullptr || atoi(e_ws) != 0) && layer_order && d->taps == 1 && bn == 256 && L.w[W_KBLOCKS] <= 4 && L.w[W_NTILES] >= 2 &&
-          grid0 % L.w[W_NTILES] == 0 && d->N % 256 == 0)
+      const int w_units = d->taps * L.w[W_KBLOCKS] * (bn >> 6);        // resident weight tile, in 8 KB units; >= 8 units stay for the ring
+      const int ws_mode = e_ws ? atoi(e_ws) : 1;                        // 1: conv3-type layers only (several N tiles); 2: every layer whose tile fits
+      if (ws_mode != 0 && layer_order && w_units <= 16 && d->N % bn == 0 && grid0 % L.w[W_NTILES] == 0 &&
+          (ws_mode == 2 || (d->taps == 1 && bn == 256 && L.w[W_NTILES] >= 2)))
         L.w[W_HAS_RES] |= 2;
     }
     L.w[W_CNT_OFF] = cnt_off;
