@@ -275,6 +275,13 @@ int lvcb200_match_boxes(const float* gt_boxes, int64_t G, const float* boxes, co
                         int allow_low_quality_matches, int64_t* matches, int8_t* match_labels, float* matched_vals, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* RPN.losses (detectron2/modeling/proposal_generator/rpn.py:328-400) before normalisation and loss weights: out2[0] = sum of
+ * binary_cross_entropy_with_logits over anchors with gt_labels >= 0, out2[1] = sum of smooth_l1(pred_anchor_deltas -
+ * Box2BoxTransform(weights).get_deltas(anchors, gt_boxes), beta) over gt_labels == 1 (beta < 1e-5: L1).  anchors [A,4] (all levels
+ * concatenated), logits [N,A], deltas [N,A,4], gt_labels [N,A] int8, gt_boxes [N,A,4] (matched gt per anchor), out2: 2 device doubles. */
+int lvcb200_rpn_losses(const float* anchors, const float* logits, const float* deltas, const int8_t* gt_labels, const float* gt_boxes,
+                       int64_t N, int64_t A, const float* weights /*host [4]*/, float smooth_l1_beta, double* out2, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -86,6 +86,8 @@ _SIGS = {
     "lvcb200_match_boxes_workspace": (c_size_t, [c_int64]),
     "lvcb200_match_boxes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8), c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lvcb200_rpn_losses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_float), c_float, c_void_p,
+                                   c_void_p]),
     "lvcb200_stem_s2d4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_maxpool_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_crops_qe": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -120,6 +120,43 @@ match_low_quality_kernel(const float4* __restrict__ gt, int64_t G, const float4*
   if (hit) labels[p] = 1;
 }
 
+// RPN.losses (rpn.py:328-400) before normalisation: objectness BCE-with-logits over anchors with label >= 0, smooth-L1 (beta < 1e-5: L1)
+// between the predicted deltas and Box2BoxTransform.get_deltas(anchor, matched gt) (box_regression.py:38-71) over label == 1.
+// Thread per (image, anchor), coalesced 16-byte loads of deltas / gt boxes; fp64 block reduction, one atomicAdd(double) pair per CTA.
+__global__ void __launch_bounds__(256)
+rpn_losses_kernel(const float4* __restrict__ anchors, const float* __restrict__ logits, const float4* __restrict__ deltas,
+                  const int8_t* __restrict__ labels, const float4* __restrict__ gt, int64_t N, int64_t A, float4 w, float beta,
+                  double* __restrict__ out2) {
+  double cls = 0.0, loc = 0.0;
+  const int64_t total = N * A;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int8_t l = labels[i];
+    if (l >= 0) {
+      const float x = logits[i], y = (float)l;
+      cls += (double)(fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))));
+    }
+    if (l == 1) {
+      const float4 s = __ldg(anchors + (i % A)), t = gt[i], d = deltas[i];
+      const float sw = s.z - s.x, sh = s.w - s.y, sx = s.x + 0.5f * sw, sy = s.y + 0.5f * sh;
+      const float tw = t.z - t.x, th = t.w - t.y, tx = t.x + 0.5f * tw, ty = t.y + 0.5f * th;
+      const float e[4] = {fabsf(d.x - w.x * (tx - sx) / sw), fabsf(d.y - w.y * (ty - sy) / sh), fabsf(d.z - w.z * logf(tw / sw)),
+                          fabsf(d.w - w.w * logf(th / sh))};
+#pragma unroll
+      for (int k = 0; k < 4; k++) loc += (double)(beta < 1e-5f ? e[k] : (e[k] < beta ? 0.5f * e[k] * e[k] / beta : e[k] - 0.5f * beta));
+    }
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o; o >>= 1) { cls += __shfl_xor_sync(0xffffffffu, cls, o); loc += __shfl_xor_sync(0xffffffffu, loc, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cls; red[1][threadIdx.x >> 5] = loc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; i++) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(out2, a);
+    atomicAdd(out2 + 1, b);
+  }
+}
+
 }  // namespace lvcb200
 
 using namespace lvcb200;
@@ -186,4 +223,20 @@ extern "C" int lvcb200_match_boxes(const float* gt_boxes, int64_t G, const float
   match_low_quality_kernel<<<blocks, 256, 0, s>>>((const float4*)gt_boxes, G, (const float4*)boxes, quality, P,
                                                   (const unsigned int*)workspace, match_labels);
   return check_launch("match_low_quality_kernel");
+}
+
+extern "C" int lvcb200_rpn_losses(const float* anchors, const float* logits, const float* deltas, const int8_t* labels,
+                                  const float* gt_boxes, int64_t N, int64_t A, const float* weights, float smooth_l1_beta,
+                                  double* out2, void* stream) {
+  LVC_REQUIRE(N >= 0 && A >= 0 && weights && out2, "rpn_losses: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  LVC_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), s));
+  if (N * A == 0) return 0;
+  LVC_REQUIRE(anchors && logits && deltas && labels && gt_boxes, "rpn_losses: NULL pointer");
+  LVC_REQUIRE(((uintptr_t)anchors % 16) == 0 && ((uintptr_t)deltas % 16) == 0 && ((uintptr_t)gt_boxes % 16) == 0, "rpn_losses: boxes / deltas must be 16-byte aligned");
+  int64_t blocks = ceil_div64(N * A, 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  rpn_losses_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float4*)anchors, logits, (const float4*)deltas, labels, (const float4*)gt_boxes, N, A,
+                                                     make_float4(weights[0], weights[1], weights[2], weights[3]), smooth_l1_beta, out2);
+  return check_launch("rpn_losses_kernel");
 }

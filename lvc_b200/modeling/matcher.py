@@ -64,3 +64,24 @@ class Matcher:
         _lib.require_cuda(g, b)
         g, b = g.detach().to(torch.float32).contiguous(), b.detach().to(torch.float32).contiguous()
         return self._run(g if g.shape[0] else None, b, None, g.shape[0], b.shape[0], b.device)
+
+
+def rpn_losses(anchors, pred_objectness_logits, pred_anchor_deltas, gt_labels, gt_boxes, batch_size_per_image=256,
+               box2box_weights=(1.0, 1.0, 1.0, 1.0), smooth_l1_beta=0.0, loss_weight=None):
+    """RPN.losses (rpn.py:328-400), smooth-L1 flavour: anchors [A,4] (levels concatenated), logits [N,A], deltas [N,A,4], gt_labels [N,A]
+    (int8: -1 ignore / 0 / 1), gt_boxes [N,A,4] -> {"loss_rpn_cls", "loss_rpn_loc"} (0-d CUDA tensors)."""
+    a = getattr(anchors, "tensor", anchors)
+    _lib.require_cuda(a, pred_objectness_logits, pred_anchor_deltas, gt_labels, gt_boxes)
+    a = a.detach().to(torch.float32).contiguous()
+    lg = pred_objectness_logits.detach().to(torch.float32).contiguous()
+    dl = pred_anchor_deltas.detach().to(torch.float32).contiguous()
+    lb = gt_labels.detach().to(torch.int8).contiguous()
+    gb = gt_boxes.detach().to(torch.float32).contiguous()
+    N, A = lg.shape
+    out = torch.zeros(2, dtype=torch.float64, device=lg.device)
+    w = (ctypes.c_float * 4)(*box2box_weights)
+    _lib.check(_lib.load().lvcb200_rpn_losses(_lib.ptr(a), _lib.ptr(lg), _lib.ptr(dl), _lib.ptr(lb), _lib.ptr(gb), N, A, w, float(smooth_l1_beta),
+                                              _lib.ptr(out), _lib.stream_ptr()), "lvcb200_rpn_losses")
+    norm = float(batch_size_per_image * N)
+    lw = loss_weight or {}
+    return {"loss_rpn_cls": (out[0] / norm).float() * lw.get("loss_rpn_cls", 1.0), "loss_rpn_loc": (out[1] / norm).float() * lw.get("loss_rpn_loc", 1.0)}

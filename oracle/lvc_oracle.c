@@ -441,3 +441,34 @@ ORC_API void orc_match_boxes(const float* gt, int64_t G, const float* boxes, int
       for (int64_t p = 0; p < P; p++) if (orc_iou_pair(gt + 4 * g, boxes + 4 * p) == hi) match_labels[p] = 1;
     }
 }
+
+/* RPN.losses (detectron2/modeling/proposal_generator/rpn.py:328-400) before normalisation: the two sums
+ *   objectness = sum over anchors with label >= 0 of binary_cross_entropy_with_logits(logit, label)      (:387-392)
+ *   localization = sum over anchors with label == 1 of smooth_l1(pred_delta - get_deltas(anchor, gt_box), beta)   (:367-376)
+ * with Box2BoxTransform.get_deltas (box_regression.py:38-71) and fvcore's smooth_l1_loss (beta < 1e-5 -> L1).  Accumulated in
+ * double; the reference sums fp32 tensors with torch's pairwise reduction, so parity is to ~1e-6 relative. */
+ORC_API void orc_rpn_losses(const float* anchors, const float* logits, const float* deltas, const int8_t* labels,
+                            const float* gt_boxes, int64_t N, int64_t A, const float* weights, float beta, double* out2) {
+  double cls = 0.0, loc = 0.0;
+  for (int64_t n = 0; n < N; n++)
+    for (int64_t a = 0; a < A; a++) {
+      const int8_t l = labels[n * A + a];
+      if (l >= 0) {
+        float x = logits[n * A + a], y = (float)l;
+        float mx = x > 0.f ? x : 0.f;
+        cls += (double)(mx - x * y + log1pf(expf(-fabsf(x))));
+      }
+      if (l == 1) {
+        const float* s = anchors + 4 * a;
+        const float* t = gt_boxes + 4 * (n * A + a);
+        float sw = s[2] - s[0], sh = s[3] - s[1], sx = s[0] + 0.5f * sw, sy = s[1] + 0.5f * sh;
+        float tw = t[2] - t[0], th = t[3] - t[1], tx = t[0] + 0.5f * tw, ty = t[1] + 0.5f * th;
+        float d[4] = {weights[0] * (tx - sx) / sw, weights[1] * (ty - sy) / sh, weights[2] * logf(tw / sw), weights[3] * logf(th / sh)};
+        for (int k = 0; k < 4; k++) {
+          float nn = fabsf(deltas[4 * (n * A + a) + k] - d[k]);
+          loc += (double)(beta < 1e-5f ? nn : (nn < beta ? 0.5f * nn * nn / beta : nn - 0.5f * beta));
+        }
+      }
+    }
+  out2[0] = cls; out2[1] = loc;
+}

@@ -379,6 +379,33 @@ def gold_training_ops():
                     f"{tag}_matches": m, f"{tag}_labels": l})
     m0, l0 = Matcher([0.5], [0, 1])(pairwise_iou(Boxes(torch.zeros(0, 4)), Boxes(torch.from_numpy(props[:5]))))
     out.update(empty_matches=m0, empty_labels=l0)
+    # RPN.losses (rpn.py:328-400) through the reference's own method on a stand-in `self` (the two loss terms before the
+    # loss weights; normaliser = batch_size_per_image * num_images), for beta = 0 (L1, the Base-RCNN-FPN default) and beta = 1/9
+    import types
+    from detectron2.modeling.box_regression import Box2BoxTransform
+    from detectron2.modeling.proposal_generator.rpn import RPN
+    from detectron2.utils.events import EventStorage
+    Nn, per_level = 2, [900, 300, 75]
+    A = sum(per_level)
+    anc = coco_like_boxes(rng, A)
+    gtb = anc[None] + rng.uniform(-12, 12, (Nn, A, 4)).astype(np.float32)
+    gtb[..., 2:] = np.maximum(gtb[..., 2:], gtb[..., :2] + 2.0)
+    labels = rng.choice(np.array([-1, 0, 1], np.int8), size=(Nn, A), p=[0.5, 0.4, 0.1])
+    logits = (rng.standard_normal((Nn, A)) * 3).astype(np.float32)
+    dl = (rng.standard_normal((Nn, A, 4)) * 0.5).astype(np.float32)
+    out.update(loss_anchors=anc, loss_gt_boxes=gtb, loss_labels=labels, loss_logits=logits, loss_deltas=dl)
+    offs = np.cumsum([0] + per_level)
+    for tag, beta in (("l1", 0.0), ("sl1", 1.0 / 9)):
+        me = types.SimpleNamespace(box_reg_loss_type="smooth_l1", box2box_transform=Box2BoxTransform(weights=(1.0, 1.0, 1.0, 1.0)),
+                                   smooth_l1_beta=beta, batch_size_per_image=256, loss_weight={})
+        with EventStorage(0):
+            ls = RPN.losses(me, [Boxes(torch.from_numpy(anc[offs[i]:offs[i + 1]])) for i in range(3)],
+                            [torch.from_numpy(logits[:, offs[i]:offs[i + 1]]) for i in range(3)],
+                            [torch.from_numpy(labels[n]) for n in range(Nn)],
+                            [torch.from_numpy(dl[:, offs[i]:offs[i + 1]]) for i in range(3)],
+                            [torch.from_numpy(gtb[n]) for n in range(Nn)])
+        out[f"loss_{tag}"] = np.array([float(ls["loss_rpn_cls"]), float(ls["loss_rpn_loc"])], np.float64) * (256 * Nn)
+        out[f"loss_{tag}_beta"] = np.float32(beta)
     save("training_ops", **out)
 
 

@@ -423,3 +423,14 @@ def match_boxes(gt, boxes, thresholds, labels, allow_low_quality):
                           lb.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), int(bool(allow_low_quality)), _p(m, _i64p),
                           l.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(v, _f32p))
     return m, l, v
+
+
+def rpn_losses(anchors, logits, deltas, labels, gt_boxes, weights=(1.0, 1.0, 1.0, 1.0), beta=0.0):
+    """The two un-normalised sums of RPN.losses (rpn.py:328-400): (objectness BCE, localisation smooth-L1)."""
+    a, lg, dl, gb = _f32(anchors), _f32(logits), _f32(deltas), _f32(gt_boxes)
+    lb = np.ascontiguousarray(labels, np.int8)
+    N, A = lg.shape
+    out = np.zeros(2, np.float64)
+    lib().orc_rpn_losses(_p(a, _f32p), _p(lg, _f32p), _p(dl, _f32p), lb.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(gb, _f32p),
+                         ctypes.c_int64(N), ctypes.c_int64(A), _p(_f32(weights), _f32p), ctypes.c_float(beta), _p(out, _f64p))
+    return out

@@ -349,6 +349,16 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
             for n in names:
                 setattr(m, n, type(n, (_Anything,), {}))
             m.__all__ = names
+        elif name == "fvcore.nn":
+            # fvcore is a third-party dependency that is not vendored in the reference (setup.py: fvcore>=0.1.1).  Its published
+            # smooth_l1_loss (fvcore/nn/smooth_l1_loss.py) is restated here so that the reference's own RPN.losses (rpn.py:328-400)
+            # can be executed to generate fixtures: beta < 1e-5 -> L1, else 0.5 n^2 / beta below beta and n - 0.5 beta above.
+            def smooth_l1_loss(input, target, beta, reduction="none"):
+                import torch
+                n = torch.abs(input - target)
+                loss = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
+                return loss.mean() if reduction == "mean" else loss.sum() if reduction == "sum" else loss
+            m.smooth_l1_loss = smooth_l1_loss
         elif name == "termcolor":
             m.colored = lambda s, *a, **k: s
         elif name == "pycocotools.coco":

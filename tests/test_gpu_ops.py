@@ -349,3 +349,25 @@ def test_pairwise_iou_and_matcher(golden):
     wm, wl, _ = O.match_boxes(gtb, anc, [0.3, 0.7], [0, -1, 1], True)
     m, l = Matcher([0.3, 0.7], [0, -1, 1], True).match_boxes(torch.from_numpy(gtb).to(DEV), torch.from_numpy(anc).to(DEV))
     assert np.array_equal(m.cpu().numpy(), wm) and np.array_equal(l.cpu().numpy(), wl)
+
+
+def test_rpn_losses(golden):
+    """lvcb200_rpn_losses vs the reference's RPN.losses (fixture) and vs the oracle at the full anchor count; 1e-5 relative (fp32 terms)."""
+    from lvc_b200.modeling import rpn_losses
+    g = golden("training_ops")
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    for tag in ("l1", "sl1"):
+        ls = rpn_losses(t("loss_anchors"), t("loss_logits"), t("loss_deltas"), t("loss_labels"), t("loss_gt_boxes"), 256, smooth_l1_beta=float(g[f"loss_{tag}_beta"]))
+        want = g[f"loss_{tag}"] / (256 * 2)
+        assert abs(float(ls["loss_rpn_cls"]) - want[0]) <= 1e-5 * want[0] and abs(float(ls["loss_rpn_loc"]) - want[1]) <= 1e-5 * want[1], tag
+    rng = np.random.default_rng(5)
+    N, A = 2, 268569
+    anc = coco_like_boxes(rng, A)
+    gtb = anc[None] + rng.uniform(-10, 10, (N, A, 4)).astype(np.float32)
+    gtb[..., 2:] = np.maximum(gtb[..., 2:], gtb[..., :2] + 2.0)
+    lab = rng.choice(np.array([-1, 0, 1], np.int8), size=(N, A), p=[0.9, 0.08, 0.02])
+    lg = (rng.standard_normal((N, A)) * 2).astype(np.float32)
+    dl = (rng.standard_normal((N, A, 4)) * 0.3).astype(np.float32)
+    want = O.rpn_losses(anc, lg, dl, lab, gtb, beta=0.0) / (256 * N)
+    ls = rpn_losses(*[torch.from_numpy(v).to(DEV) for v in (anc, lg, dl, lab, gtb)], 256)
+    assert abs(float(ls["loss_rpn_cls"]) - want[0]) <= 1e-5 * want[0] and abs(float(ls["loss_rpn_loc"]) - want[1]) <= 1e-5 * want[1]
