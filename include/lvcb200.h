@@ -209,6 +209,10 @@ typedef struct {
   int taps; int32_t shift[9];                   /* row shift per tap */
   int relu;
   int plane_h, plane_w;                         /* 0 = no border masking */
+  /* optional (appended; NULL = off): FPN top-down path fused into the lateral conv (fpn.py:128-134): D += nearest-2x-upsample(up),
+   * up = the coarser level's zero-bordered bf16 plane [n, up_plane_h, up_plane_w, >= N] (row pitch ldu elements), this plane being
+   * exactly twice its interior size.  bf16 output, N % 64 == 0, no residual; added in fp32 before the single bf16 rounding. */
+  const void* upsample_add; int64_t ldu; int up_plane_h, up_plane_w;
 } lvcb200_gemm_desc;
 
 int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d /*host*/, void* stream);

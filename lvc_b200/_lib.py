@@ -41,7 +41,8 @@ class GemmDesc(Structure):
     _fields_ = [("a_dtype", c_int), ("A", c_void_p), ("lda", c_int64), ("M_rows", c_int64), ("W", c_void_p), ("ldw", c_int64),
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64), ("D", c_void_p), ("ldd", c_int64),
                 ("d_dtype", c_int), ("M", c_int64), ("N", c_int), ("K", c_int), ("taps", c_int), ("shift", c_int32 * 9),
-                ("relu", c_int), ("plane_h", c_int), ("plane_w", c_int)]
+                ("relu", c_int), ("plane_h", c_int), ("plane_w", c_int),
+                ("upsample_add", c_void_p), ("ldu", c_int64), ("up_plane_h", c_int), ("up_plane_w", c_int)]
 
 
 class ChainPlan(Structure):

@@ -33,6 +33,7 @@ struct GemmParams {
   int has_res;                     // residual tile added on the tensor core: D += R_tile * I (identity B operand)
   int num_stages;                  // smem pipeline depth (runtime: deep for big-K layers, shallow + big staging for small-K)
   int phase_cols;                  // MODE 1: output columns staged per TMA-store phase (64 or 128)
+  const __nv_bfloat16* up; long long ldu; int up_ph, up_pw;   // UPS instantiation: D += nearest-2x-upsample(up) (FPN top-down add)
   int warp_epi;                    // MODE 1: warp-private staging + one TMA store per warp per 64 columns (no CTA-wide barriers)
   int debug;                       // experiments only, bit mask: 1 = issue no MMAs, 2 = issue no TMA loads, 4 = issue no TMA stores (results are garbage)
 };
@@ -60,7 +61,9 @@ __host__ __device__ inline int gemm_smem_bytes(int block_n, int mode, int num_st
   return b + kCtrlBytes + 1024 /*alignment slack*/;
 }
 
-template <int BLOCK_N, int MODE, int KIND>   // KIND 0: bf16 operands (kind::f16); KIND 1: fp32 operands as tf32 (kind::tf32)
+// KIND 0: bf16 operands (kind::f16); KIND 1: fp32 operands as tf32 (kind::tf32).  UPS 1: the epilogue adds the 2x-upsampled coarser FPN
+// level (its own instantiation: the other layers' code is untouched).
+template <int BLOCK_N, int MODE, int KIND, int UPS = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -231,11 +234,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if constexpr (MODE == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       const long long m = (long long)m0 + q * 32 + lane;
       bool zero_row = false;
+      [[maybe_unused]] const __nv_bfloat16* up_row = nullptr;
       if (p.plane_h > 0) {
         unsigned int plane = (unsigned)(p.plane_h * p.plane_w);
         unsigned int rem = (unsigned int)((unsigned long long)m % plane);
         unsigned int y = rem / (unsigned)p.plane_w, x = rem - y * (unsigned)p.plane_w;
         zero_row = (y == 0) || (y == (unsigned)p.plane_h - 1) || (x == 0) || (x == (unsigned)p.plane_w - 1);
+        if constexpr (UPS) {   // row of the coarser plane under this pixel: interior (y, x) -> ((y - 1) / 2 + 1, (x - 1) / 2 + 1)
+          const long long img = m / plane;
+          up_row = zero_row ? nullptr
+                            : p.up + ((img * p.up_ph + (long long)(((y - 1) >> 1) + 1)) * p.up_pw + (((x - 1) >> 1) + 1)) * p.ldu + n0;
+        }
       }
       if (lane == 0) mbar_wait(bar_tfull + 8 * b, bph);   // one poller per warp keeps the mbarrier unit free for the TMA / MMA threads
       __syncwarp();
@@ -372,9 +381,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
+                [[maybe_unused]] uint4 ut = make_uint4(0, 0, 0, 0);
+                if constexpr (UPS) { if (up_row != nullptr) ut = __ldg(reinterpret_cast<const uint4*>(up_row + c + 8 * j)); }
+                [[maybe_unused]] const uint32_t* uw = &ut.x;
                 for (int e = 0; e < 4; e++) {
                   float a0 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e]) + bb[2 * e];
                   float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
+                  if constexpr (UPS) { a0 += __uint_as_float(uw[e] << 16); a1 += __uint_as_float(uw[e] & 0xffff0000u); }
                   if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
                   if (zero_row) { a0 = 0.f; a1 = 0.f; }
                   if (p.d_f16) { __half2 hh = __floats2half2_rn(a0, a1); ho[e] = *reinterpret_cast<__nv_bfloat162*>(&hh); }
@@ -661,12 +674,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 }
 
 
-template <int BLOCK_N, int MODE, int KIND = 0>
+template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
                        cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res);
@@ -684,9 +697,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND>, ta, tw, td, tr, p));
+    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS>, ta, tw, td, tr, p));
   } else {
-    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   }
   return check_launch("gemm_bf16_tc_kernel");
 }
@@ -780,9 +793,17 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (p.num_stages > kMaxStages) p.num_stages = kMaxStages;
   if (!deep && p.num_stages > 4) p.num_stages = 4;
   p.debug = 0;
+  p.up = (const __nv_bfloat16*)d->upsample_add; p.ldu = d->ldu; p.up_ph = d->up_plane_h; p.up_pw = d->up_plane_w;
+  if (p.up) {
+    LVC_REQUIRE(mode == 1 && !tf32 && !d->residual && d->N % 64 == 0 && d->plane_h > 2 && d->plane_w > 2 && d->d_dtype == LVCB200_BF16,
+                "gemm: upsample_add needs a bf16 plane output, N % 64 == 0, no residual");
+    LVC_REQUIRE(d->plane_h - 2 == 2 * (d->up_plane_h - 2) && d->plane_w - 2 == 2 * (d->up_plane_w - 2) && d->ldu % 8 == 0 &&
+                ((uintptr_t)d->upsample_add % 16) == 0, "gemm: upsample_add: the coarse plane must be exactly half the size (fpn.py:131), 16-byte aligned");
+    LVC_REQUIRE(bn == 256, "gemm: upsample_add is built for N >= 256 (FPN laterals)");
+  }
   {
     static const char* e_we = getenv("LVCB200_GEMM_WEPI");
-    p.warp_epi = (mode == 1 && e_we != nullptr && atoi(e_we) != 0 && ((uintptr_t)d->bias % 16) == 0) ? 1 : 0;   // experiment: same speed as the shared-phase epilogue (profiles/r01_gemm_modes.md)
+    p.warp_epi = (mode == 1 && !p.up && e_we != nullptr && atoi(e_we) != 0 && ((uintptr_t)d->bias % 16) == 0) ? 1 : 0;   // experiment: same speed as the shared-phase epilogue (profiles/r01_gemm_modes.md)
   }
   {  // tuning overrides for experiments (tools/gemm_sweep.py); not used by the engine
     static const char* e_dbg = getenv("LVCB200_GEMM_DEBUG");
@@ -810,7 +831,7 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
     const int two_cta = e_2 ? atoi(e_2) : 2;   // default: 2-CTA tiles for the big 3x3 convs only (same-box A/B: dense stack -1.7 % sustained)
     // 1: every eligible layer; 2 (default): long K loops on wide tiles -- the big 3x3 convs and the fc layers (per-shape table in
     // profiles/r01_gemm_modes.md: the pair handshake is amortised and half the B bytes per SM buy two more ring stages); 3: big 3x3 only
-    const bool want2 = two_cta == 1 || (two_cta == 3 && d->taps == 9 && bn == 256 && d->M >= 100000) ||
+    const bool want2 = p.up ? false : two_cta == 1 || (two_cta == 3 && d->taps == 9 && bn == 256 && d->M >= 100000) ||
                        (two_cta == 2 && bn == 256 && !p.has_res && k_iters >= 16 && (d->M >= 100000 || (d->taps == 1 && d->M >= 8000)));
     if (want2 && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
       GemmParams p2 = p;
@@ -829,6 +850,7 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
       }
     }
   }
+  if (p.up) return launch_gemm<256, 1, 0, 1>(ta, tw, td, tr, p, s);
   const CUtensorMap& tdu = p.warp_epi ? td32 : td;
   if (tf32) return bn == 256 ? launch_gemm<256, 1, 1>(ta, tw, tdu, tr, p, s) : launch_gemm<128, 1, 1>(ta, tw, tdu, tr, p, s);
   switch (bn) {

@@ -129,6 +129,7 @@ class DetectorEngine:
         # res stages run as layer-chain launches (gemm_chain.cu).  res2 stays on per-layer launches: its N = 64 layers issue one tiny
         # MMA group per 24 KB operand block, which the leaner single-layer producer loop feeds faster (profiles/r01_gemm_layers_*.md)
         self.use_chain = os.environ.get("LVCB200_CHAIN", "1") != "0"
+        self.fuse_upsample = os.environ.get("LVCB200_FUSE_UPSAMPLE", "0") != "0"   # same step time as the separate kernel in a same-box A/B: off
         self.chain_stages = tuple(int(x) for x in os.environ.get("LVCB200_CHAIN_STAGES", "3,4,5").split(",") if x)
         self._bufs = {}
         self._graphs = {}
@@ -147,7 +148,8 @@ class DetectorEngine:
         return ops.Plane(self._buf(name, (n, H + 2, W + 2, C), dtype), H, W, C)
 
     # ------------------------------------------------------------------ layers
-    def _conv(self, name, x: ops.Plane, conv: _Conv, residual: Optional[ops.Plane] = None, out_dtype=torch.bfloat16):
+    def _conv(self, name, x: ops.Plane, conv: _Conv, residual: Optional[ops.Plane] = None, out_dtype=torch.bfloat16,
+              upsample_add: Optional[ops.Plane] = None):
         n = x.n
         out = self._plane(name, n, x.H, x.W, conv.cout, out_dtype)
         PW = x.PW
@@ -157,7 +159,8 @@ class DetectorEngine:
         else:
             shifts, taps = (0,), 1
         ops.gemm(x.t.view(-1, x.C), conv.w, bias=conv.b, residual=residual.t.view(-1, conv.cout) if residual is not None else None,
-                 out=out.t.view(-1, conv.cout), relu=conv.relu, taps=taps, shifts=shifts, K=conv.cin, plane_hw=(x.PH, x.PW))
+                 out=out.t.view(-1, conv.cout), relu=conv.relu, taps=taps, shifts=shifts, K=conv.cin, plane_hw=(x.PH, x.PW),
+                 upsample_add=upsample_add)
         return out
 
     def _subsample(self, name, x: ops.Plane):
@@ -204,8 +207,11 @@ class DetectorEngine:
         out = {}
         prev = None
         for l in (5, 4, 3, 2):
-            lat = self._conv(f"lat{l}", feats[l], self.lateral[l])
-            if prev is not None:
+            # top-down path (fpn.py:128-134): the nearest-2x upsampling of the coarser level is added in the lateral conv's epilogue
+            # (one rounding to bf16) when LVCB200_FUSE_UPSAMPLE=1; default: the separate read-modify-write kernel (measured equal)
+            fuse = prev is not None and self.fuse_upsample
+            lat = self._conv(f"lat{l}", feats[l], self.lateral[l], upsample_add=prev if fuse else None)
+            if prev is not None and not fuse:
                 _lib.check(lib.lvcb200_upsample2_add(_lib.ptr(prev.t), prev.n, prev.H, prev.W, 256, _lib.ptr(lat.t), lat.H, lat.W,
                                                      _lib.stream_ptr()), "upsample2_add")
             prev = lat

@@ -45,11 +45,11 @@ class gemm_chain:
 
 def _desc_key(d):
     return (d.a_dtype, d.A, d.lda, d.M_rows, d.W, d.ldw, d.bias, d.residual, d.ldr, d.D, d.ldd, d.d_dtype, d.M, d.N, d.K, d.taps,
-            tuple(d.shift), d.relu, d.plane_h, d.plane_w)
+            tuple(d.shift), d.relu, d.plane_h, d.plane_w, d.upsample_add)
 
 
 def chain_eligible(d):
-    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0
+    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0 and not d.upsample_add
 
 
 def run_chain(rec, record=True):
@@ -334,9 +334,10 @@ class KnnBank:
 
 # ---------------------------------------------------------------------------------------------- dense
 def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, relu=False, taps=1, shifts=(0,), K=None,
-         M=None, plane_hw=None):
+         M=None, plane_hw=None, upsample_add=None):
     """D = act(sum_t A[m+shift_t, :K] @ W[:, t*K:(t+1)*K]^T + bias + residual).  A [rows, >=K] bf16 (row pitch = stride(0)),
-    W [N, taps*K] bf16.  plane_hw=(PH, PW) zeroes border rows of a zero-bordered plane."""
+    W [N, taps*K] bf16.  plane_hw=(PH, PW) zeroes border rows of a zero-bordered plane.  upsample_add: a coarser Plane (half the
+    interior size) whose nearest-2x upsampling is added in the epilogue (FPN top-down path, fpn.py:128-134)."""
     _lib.require_cuda(A, W, bias, residual, out)
     assert A.dtype == W.dtype and A.dtype in (torch.bfloat16, torch.float32) and A.stride(1) == 1 and W.stride(1) == 1
     N = W.shape[0]
@@ -357,11 +358,16 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
         d.shift[i] = int(s)
     d.relu = int(relu)
     d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
+    if upsample_add is not None:
+        _lib.require_cuda(upsample_add.t)
+        d.upsample_add, d.ldu = upsample_add.t.data_ptr(), upsample_add.c_stride
+        d.up_plane_h, d.up_plane_w = upsample_add.PH, upsample_add.PW
     if GEMM_CHAIN is not None:
+        assert upsample_add is None, "upsample_add layers are not chainable"
         GEMM_CHAIN.append((d, (A, W, bias, residual, out)))
         return out
     if GEMM_RECORD is not None:
-        GEMM_RECORD.append((d, (A, W, bias, residual, out)))   # keep the tensors alive with the descriptor
+        GEMM_RECORD.append((d, (A, W, bias, residual, out, upsample_add)))   # keep the tensors alive with the descriptor
     if GEMM_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

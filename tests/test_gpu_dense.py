@@ -168,3 +168,22 @@ def test_layer_chain_rejects_in_chain_overwrite():
         with ops.gemm_chain():
             ops.gemm(a, w, out=b)
             ops.gemm(b, w, out=a)        # overwrites a buffer layer 0 reads
+
+
+def test_lateral_conv_with_fused_topdown_add():
+    """FPN lateral 1x1 conv with the nearest-2x upsampled coarser level added in the epilogue (fpn.py:128-134): against an fp32 torch
+    reference on the same bf16 operands (one bf16 rounding), borders re-zeroed."""
+    g = torch.Generator(device="cpu").manual_seed(21)
+    n, Ht, Wt, Cin, Cout = 2, 13, 21, 512, 256
+    H, W = 2 * Ht, 2 * Wt
+    x = torch.randn(n, Cin, H, W, generator=g).bfloat16().to(DEV)
+    top = torch.randn(n, Cout, Ht, Wt, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(Cout, Cin, generator=g) / Cin ** 0.5).bfloat16().to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    px, pt = ops.Plane.from_nchw(x), ops.Plane.from_nchw(top)
+    out = ops.gemm(px.t.view(-1, Cin), w, bias=bias, plane_hw=(H + 2, W + 2), upsample_add=pt)
+    po = ops.Plane(out.view(n, H + 2, W + 2, Cout), H, W, Cout)
+    want = F.conv2d(x.float(), w.float().view(Cout, Cin, 1, 1), bias) + F.interpolate(top.float(), scale_factor=2, mode="nearest")
+    _close(po.to_nchw(), want, True)
+    full = out.view(n, H + 2, W + 2, Cout).float()
+    assert float(full[:, 0].abs().max()) == 0 and float(full[:, -1].abs().max()) == 0 and float(full[:, :, 0].abs().max()) == 0
