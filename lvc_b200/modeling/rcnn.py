@@ -22,6 +22,7 @@ class GeneralizedRCNN:
         self.device = torch.device(device)
         self.engine = DetectorEngine(cfg, state_dict, device, use_cuda_graph=use_cuda_graph)
         self.training = False
+        self._host_ring = {}
 
     def eval(self):
         return self
@@ -56,7 +57,12 @@ class GeneralizedRCNN:
             main.wait_event(ready)
             boxes, scores, classes, rows, counts = self.engine.run(images, outs)
             packed = torch.cat([boxes.view(len(images), -1), scores, classes.float(), counts.float()[:, None]], dim=1)
-            host = torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True)
+            # two persistent pinned result buffers per shape, used alternately (a fresh pinned allocation per batch is a cudaHostAlloc:
+            # milliseconds, and it serialises with the device on some hosts)
+            key = (tuple(packed.shape), packed.dtype)
+            ring = self._host_ring.setdefault(key, [torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True) for _ in range(2)] + [0])
+            host = ring[ring[2] & 1]
+            ring[2] += 1
             host.copy_(packed, non_blocking=True)
             done = main.record_event()
             if pending is not None:
