@@ -91,7 +91,8 @@ def fpn(cfg, sd, feats):
     res = {}
     prev = None
     for lvl in (5, 4, 3, 2):
-        lat = _conv_bn(sd, f"backbone.fpn_lateral{lvl}", feats[f"res{lvl}"])
+        # engine policy: the top-down add happens in fp32 in the lateral conv's epilogue, ONE rounding to bf16 (quant_out=False here)
+        lat = _conv_bn(sd, f"backbone.fpn_lateral{lvl}", feats[f"res{lvl}"], quant_out=prev is None)
         if prev is not None:
             lat = _q(lat + F.interpolate(prev, scale_factor=2, mode="nearest"))
         prev = lat
