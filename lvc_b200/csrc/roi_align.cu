@@ -288,6 +288,9 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
               sTbl[wib][e] = make_int2(ry * rs + rx * cs, __float_as_int(e < n ? wyp[ry] * wxp[rx] : 0.f));
             }
             __syncwarp();
+            float2 acc2[V / 2];                 // packed fp32x2 FMAs (FFMA2, sm_100): half the FMA issue slots of this issue-bound loop
+#pragma unroll
+            for (int i = 0; i < V / 2; i++) acc2[i] = make_float2(acc[2 * i], acc[2 * i + 1]);
             for (int i0 = 0; act && i0 < npad; i0 += LB) {
               uint4 raw[LB];
               float w[LB];
@@ -301,10 +304,13 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
               for (int u = 0; u < LB; u++) {
                 float v[V];
                 Vec<TI>::unpack(raw[u], v);
+                const float2 ww = make_float2(w[u], w[u]);
 #pragma unroll
-                for (int i = 0; i < V; i++) acc[i] += w[u] * v[i];
+                for (int i = 0; i < V / 2; i++) acc2[i] = __ffma2_rn(ww, make_float2(v[2 * i], v[2 * i + 1]), acc2[i]);
               }
             }
+#pragma unroll
+            for (int i = 0; i < V / 2; i++) { acc[2 * i] = acc2[i].x; acc[2 * i + 1] = acc2[i].y; }
           }
         } else if (act) {
           roi_bin_generic<TI, V>(base, fm, g, gh, gw, ph, pw, c0, acc);
