@@ -286,6 +286,14 @@ int lvcb200_match_boxes(const float* gt_boxes, int64_t G, const float* boxes, co
 int lvcb200_rpn_losses(const float* anchors, const float* logits, const float* deltas, const int8_t* gt_labels, const float* gt_boxes,
                        int64_t N, int64_t A, const float* weights /*host [4]*/, float smooth_l1_beta, double* out2, void* stream);
 
+/* FastRCNNOutputs.losses (lvc/modeling/roi_heads/fast_rcnn.py:267-279, 296-358, 424-438) before the division by R and the loss weights:
+ * out2[0] = sum over rows of cross_entropy(cls_logits [R, K+1], gt_classes [R] int64), out2[1] = sum over foreground rows (0 <= gt < K) of
+ * smooth_l1(box_deltas[r, 4*gt .. 4*gt+3] - Box2BoxTransform(weights).get_deltas(proposals, gt_boxes), beta); n_delta_cols = 4*K, or 4 for
+ * class-agnostic regression.  out2: 2 device doubles. */
+int lvcb200_fast_rcnn_losses(const float* cls_logits, const float* box_deltas, int n_delta_cols, const int64_t* gt_classes,
+                             const float* proposals, const float* gt_boxes, int64_t R, int num_classes, const float* weights /*host [4]*/,
+                             float smooth_l1_beta, double* out2, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -89,6 +89,8 @@ _SIGS = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lvcb200_rpn_losses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_float), c_float, c_void_p,
                                    c_void_p]),
+    "lvcb200_fast_rcnn_losses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_float), c_float,
+                                         c_void_p, c_void_p]),
     "lvcb200_stem_s2d4": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_maxpool_s2d": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_crops_qe": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

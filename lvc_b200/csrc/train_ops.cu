@@ -157,6 +157,49 @@ rpn_losses_kernel(const float4* __restrict__ anchors, const float* __restrict__ 
   }
 }
 
+// FastRCNNOutputs.losses (lvc/modeling/roi_heads/fast_rcnn.py:267-358, 424-438) before the division by R: warp per RoI row --
+// log-sum-exp cross entropy over the K + 1 logits (lanes stride the columns), and for foreground rows the smooth-L1 / L1 distance
+// between the gt class's four predicted deltas and get_deltas(proposal, gt box).  fp64 reduction, one atomicAdd pair per CTA.
+__global__ void __launch_bounds__(256)
+fast_rcnn_losses_kernel(const float* __restrict__ logits, const float* __restrict__ deltas, int n_delta_cols, const int64_t* __restrict__ gt_classes,
+                        const float4* __restrict__ proposals, const float4* __restrict__ gt_boxes, int64_t R, int K, float4 w, float beta,
+                        double* __restrict__ out2) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double cls = 0.0, box = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + wib; r < R; r += (int64_t)gridDim.x * 8) {
+    const float* x = logits + r * (K + 1);
+    float mx = -INFINITY;
+    for (int k = lane; k <= K; k += 32) mx = fmaxf(mx, x[k]);
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int k = lane; k <= K; k += 32) se += expf(x[k] - mx);
+    for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (lane == 0) {
+      const int64_t g = gt_classes[r];
+      cls += (double)(logf(se) + mx - x[g]);
+      if (g >= 0 && g < K) {
+        const float4 s = proposals[r], t = gt_boxes[r];
+        const float sw = s.z - s.x, sh = s.w - s.y, sx = s.x + 0.5f * sw, sy = s.y + 0.5f * sh;
+        const float tw = t.z - t.x, th = t.w - t.y, tx = t.x + 0.5f * tw, ty = t.y + 0.5f * th;
+        const float* pd = deltas + r * n_delta_cols + (n_delta_cols == 4 ? 0 : 4 * g);
+        const float e[4] = {fabsf(pd[0] - w.x * (tx - sx) / sw), fabsf(pd[1] - w.y * (ty - sy) / sh), fabsf(pd[2] - w.z * logf(tw / sw)),
+                            fabsf(pd[3] - w.w * logf(th / sh))};
+#pragma unroll
+        for (int k = 0; k < 4; k++) box += (double)(beta < 1e-5f ? e[k] : (e[k] < beta ? 0.5f * e[k] * e[k] / beta : e[k] - 0.5f * beta));
+      }
+    }
+  }
+  __shared__ double red[2][8];
+  if (lane == 0) { red[0][wib] = cls; red[1][wib] = box; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; i++) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(out2, a);
+    atomicAdd(out2 + 1, b);
+  }
+}
+
 }  // namespace lvcb200
 
 using namespace lvcb200;
@@ -239,4 +282,21 @@ extern "C" int lvcb200_rpn_losses(const float* anchors, const float* logits, con
   rpn_losses_kernel<<<(unsigned)blocks, 256, 0, s>>>((const float4*)anchors, logits, (const float4*)deltas, labels, (const float4*)gt_boxes, N, A,
                                                      make_float4(weights[0], weights[1], weights[2], weights[3]), smooth_l1_beta, out2);
   return check_launch("rpn_losses_kernel");
+}
+
+extern "C" int lvcb200_fast_rcnn_losses(const float* cls_logits, const float* box_deltas, int n_delta_cols, const int64_t* gt_classes,
+                                        const float* proposals, const float* gt_boxes, int64_t R, int num_classes, const float* weights,
+                                        float smooth_l1_beta, double* out2, void* stream) {
+  LVC_REQUIRE(R >= 0 && num_classes >= 1 && weights && out2 && (n_delta_cols == 4 || n_delta_cols == 4 * num_classes), "fast_rcnn_losses: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  LVC_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), s));
+  if (R == 0) return 0;
+  LVC_REQUIRE(cls_logits && box_deltas && gt_classes && proposals && gt_boxes, "fast_rcnn_losses: NULL pointer");
+  LVC_REQUIRE(((uintptr_t)proposals % 16) == 0 && ((uintptr_t)gt_boxes % 16) == 0, "fast_rcnn_losses: boxes must be 16-byte aligned");
+  int64_t blocks = ceil_div64(R, 8);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  fast_rcnn_losses_kernel<<<(unsigned)blocks, 256, 0, s>>>(cls_logits, box_deltas, n_delta_cols, gt_classes, (const float4*)proposals,
+                                                           (const float4*)gt_boxes, R, num_classes,
+                                                           make_float4(weights[0], weights[1], weights[2], weights[3]), smooth_l1_beta, out2);
+  return check_launch("fast_rcnn_losses_kernel");
 }

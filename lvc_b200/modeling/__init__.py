@@ -1,6 +1,6 @@
 from .corrector import BoxCorrectorHead
 from .engine import DetectorEngine
-from .matcher import Matcher, pairwise_iou, rpn_losses
+from .matcher import Matcher, fast_rcnn_losses, pairwise_iou, rpn_losses
 from .rcnn import GeneralizedRCNN
 
-__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN", "Matcher", "pairwise_iou", "rpn_losses"]
+__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN", "Matcher", "fast_rcnn_losses", "pairwise_iou", "rpn_losses"]

@@ -85,3 +85,24 @@ def rpn_losses(anchors, pred_objectness_logits, pred_anchor_deltas, gt_labels, g
     norm = float(batch_size_per_image * N)
     lw = loss_weight or {}
     return {"loss_rpn_cls": (out[0] / norm).float() * lw.get("loss_rpn_cls", 1.0), "loss_rpn_loc": (out[1] / norm).float() * lw.get("loss_rpn_loc", 1.0)}
+
+
+def fast_rcnn_losses(pred_class_logits, pred_proposal_deltas, gt_classes, proposal_boxes, gt_boxes, box2box_weights=(10.0, 10.0, 5.0, 5.0),
+                     smooth_l1_beta=0.0, loss_weight=None):
+    """FastRCNNOutputs.losses (lvc/modeling/roi_heads/fast_rcnn.py:424-438), smooth-L1 flavour: logits [R,K+1], deltas [R,4K] or [R,4],
+    gt_classes [R] (K = background), proposal / gt boxes [R,4] -> {"loss_cls", "loss_box_reg"} (0-d CUDA tensors, both divided by R)."""
+    pb = getattr(proposal_boxes, "tensor", proposal_boxes)
+    gb = getattr(gt_boxes, "tensor", gt_boxes)
+    _lib.require_cuda(pred_class_logits, pred_proposal_deltas, gt_classes, pb, gb)
+    lg = pred_class_logits.detach().to(torch.float32).contiguous()
+    dl = pred_proposal_deltas.detach().to(torch.float32).contiguous()
+    gc = gt_classes.detach().to(torch.int64).contiguous()
+    pb, gb = pb.detach().to(torch.float32).contiguous(), gb.detach().to(torch.float32).contiguous()
+    R, K1 = lg.shape
+    out = torch.zeros(2, dtype=torch.float64, device=lg.device)
+    w = (ctypes.c_float * 4)(*box2box_weights)
+    _lib.check(_lib.load().lvcb200_fast_rcnn_losses(_lib.ptr(lg), _lib.ptr(dl), dl.shape[1], _lib.ptr(gc), _lib.ptr(pb), _lib.ptr(gb), R, K1 - 1, w,
+                                                    float(smooth_l1_beta), _lib.ptr(out), _lib.stream_ptr()), "lvcb200_fast_rcnn_losses")
+    lw = loss_weight or {}
+    n = float(max(R, 1))
+    return {"loss_cls": (out[0] / n).float() * lw.get("loss_cls", 1.0), "loss_box_reg": (out[1] / n).float() * lw.get("loss_box_reg", 1.0)}

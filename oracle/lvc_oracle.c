@@ -472,3 +472,35 @@ ORC_API void orc_rpn_losses(const float* anchors, const float* logits, const flo
     }
   out2[0] = cls; out2[1] = loc;
 }
+
+/* FastRCNNOutputs.losses (lvc/modeling/roi_heads/fast_rcnn.py:267-279, 296-358, 424-438) before the division by R:
+ *   cls = sum over rows of cross_entropy(logits[r, :], gt_classes[r])          (F.cross_entropy, log-sum-exp with the row maximum)
+ *   box = sum over foreground rows (0 <= gt < K) of smooth_l1(deltas[r, 4*gt : 4*gt+4] - get_deltas(proposal, gt_box), beta)
+ * class-agnostic regression when n_delta_cols == 4.  Accumulated in double. */
+ORC_API void orc_fast_rcnn_losses(const float* logits, const float* deltas, int n_delta_cols, const int64_t* gt_classes,
+                                  const float* proposals, const float* gt_boxes, int64_t R, int K, const float* weights, float beta,
+                                  double* out2) {
+  double cls = 0.0, box = 0.0;
+  for (int64_t r = 0; r < R; r++) {
+    const float* x = logits + r * (K + 1);
+    float mx = x[0];
+    for (int k = 1; k <= K; k++) mx = x[k] > mx ? x[k] : mx;
+    float se = 0.f;
+    for (int k = 0; k <= K; k++) se += expf(x[k] - mx);
+    const int64_t g = gt_classes[r];
+    cls += (double)(logf(se) + mx - x[g]);
+    if (g >= 0 && g < K) {
+      const float* s = proposals + 4 * r;
+      const float* t = gt_boxes + 4 * r;
+      float sw = s[2] - s[0], sh = s[3] - s[1], sx = s[0] + 0.5f * sw, sy = s[1] + 0.5f * sh;
+      float tw = t[2] - t[0], th = t[3] - t[1], tx = t[0] + 0.5f * tw, ty = t[1] + 0.5f * th;
+      float d[4] = {weights[0] * (tx - sx) / sw, weights[1] * (ty - sy) / sh, weights[2] * logf(tw / sw), weights[3] * logf(th / sh)};
+      const float* pd = deltas + r * n_delta_cols + (n_delta_cols == 4 ? 0 : 4 * g);
+      for (int k = 0; k < 4; k++) {
+        float nn = fabsf(pd[k] - d[k]);
+        box += (double)(beta < 1e-5f ? nn : (nn < beta ? 0.5f * nn * nn / beta : nn - 0.5f * beta));
+      }
+    }
+  }
+  out2[0] = cls; out2[1] = box;
+}

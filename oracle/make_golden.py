@@ -406,6 +406,28 @@ def gold_training_ops():
                             [torch.from_numpy(gtb[n]) for n in range(Nn)])
         out[f"loss_{tag}"] = np.array([float(ls["loss_rpn_cls"]), float(ls["loss_rpn_loc"])], np.float64) * (256 * Nn)
         out[f"loss_{tag}_beta"] = np.float32(beta)
+    # FastRCNNOutputs.losses (lvc/modeling/roi_heads/fast_rcnn.py:424-438) through the reference's own class
+    from detectron2.structures import Instances
+    from lvc.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
+    R, K = 1024, 80
+    props = coco_like_boxes(rng, R)
+    gtb2 = props + rng.uniform(-15, 15, (R, 4)).astype(np.float32)
+    gtb2[:, 2:] = np.maximum(gtb2[:, 2:], gtb2[:, :2] + 2.0)
+    gcls = np.where(rng.random(R) < 0.25, rng.integers(0, K, R), K).astype(np.int64)
+    clog = (rng.standard_normal((R, K + 1)) * 2).astype(np.float32)
+    pdel = (rng.standard_normal((R, 4 * K)) * 0.5).astype(np.float32)
+    out.update(frcnn_props=props, frcnn_gt_boxes=gtb2, frcnn_gt_classes=gcls, frcnn_logits=clog, frcnn_deltas=pdel)
+    halves = [slice(0, 600), slice(600, R)]
+    insts = []
+    for sl in halves:
+        ins = Instances((800, 1333))
+        ins.proposal_boxes, ins.gt_boxes, ins.gt_classes = Boxes(torch.from_numpy(props[sl])), Boxes(torch.from_numpy(gtb2[sl])), torch.from_numpy(gcls[sl])
+        insts.append(ins)
+    for tag, beta in (("l1", 0.0), ("sl1", 0.5)):
+        with EventStorage(0):
+            ls = FastRCNNOutputs(Box2BoxTransform(weights=(10.0, 10.0, 5.0, 5.0)), torch.from_numpy(clog), torch.from_numpy(pdel), insts, beta).losses()
+        out[f"frcnn_{tag}"] = np.array([float(ls["loss_cls"]), float(ls["loss_box_reg"])], np.float64) * R
+        out[f"frcnn_{tag}_beta"] = np.float32(beta)
     save("training_ops", **out)
 
 

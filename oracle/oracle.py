@@ -434,3 +434,14 @@ def rpn_losses(anchors, logits, deltas, labels, gt_boxes, weights=(1.0, 1.0, 1.0
     lib().orc_rpn_losses(_p(a, _f32p), _p(lg, _f32p), _p(dl, _f32p), lb.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(gb, _f32p),
                          ctypes.c_int64(N), ctypes.c_int64(A), _p(_f32(weights), _f32p), ctypes.c_float(beta), _p(out, _f64p))
     return out
+
+
+def fast_rcnn_losses(logits, deltas, gt_classes, proposals, gt_boxes, weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
+    """The two un-normalised sums of FastRCNNOutputs.losses (lvc fast_rcnn.py:267-358, 424-438): (cross entropy, box smooth-L1)."""
+    lg, dl, pr, gb = _f32(logits), _f32(deltas), _f32(proposals), _f32(gt_boxes)
+    gc = _i64(gt_classes)
+    R, K1 = lg.shape
+    out = np.zeros(2, np.float64)
+    lib().orc_fast_rcnn_losses(_p(lg, _f32p), _p(dl, _f32p), dl.shape[1], _p(gc, _i64p), _p(pr, _f32p), _p(gb, _f32p), ctypes.c_int64(R), K1 - 1,
+                               _p(_f32(weights), _f32p), ctypes.c_float(beta), _p(out, _f64p))
+    return out

@@ -371,3 +371,20 @@ def test_rpn_losses(golden):
     want = O.rpn_losses(anc, lg, dl, lab, gtb, beta=0.0) / (256 * N)
     ls = rpn_losses(*[torch.from_numpy(v).to(DEV) for v in (anc, lg, dl, lab, gtb)], 256)
     assert abs(float(ls["loss_rpn_cls"]) - want[0]) <= 1e-5 * want[0] and abs(float(ls["loss_rpn_loc"]) - want[1]) <= 1e-5 * want[1]
+
+
+def test_fast_rcnn_losses(golden):
+    """lvcb200_fast_rcnn_losses vs the reference's FastRCNNOutputs.losses (fixture): 1e-5 relative (fp32 terms, fp64 sums)."""
+    from lvc_b200.modeling import fast_rcnn_losses
+    g = golden("training_ops")
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    for tag in ("l1", "sl1"):
+        ls = fast_rcnn_losses(t("frcnn_logits"), t("frcnn_deltas"), t("frcnn_gt_classes"), t("frcnn_props"), t("frcnn_gt_boxes"),
+                              smooth_l1_beta=float(g[f"frcnn_{tag}_beta"]))
+        want = g[f"frcnn_{tag}"] / 1024
+        assert abs(float(ls["loss_cls"]) - want[0]) <= 1e-5 * want[0] and abs(float(ls["loss_box_reg"]) - want[1]) <= 1e-5 * want[1], tag
+    # class-agnostic deltas: against the oracle
+    dl4 = t("frcnn_deltas")[:, :4].contiguous()
+    want = O.fast_rcnn_losses(g["frcnn_logits"], g["frcnn_deltas"][:, :4], g["frcnn_gt_classes"], g["frcnn_props"], g["frcnn_gt_boxes"]) / 1024
+    ls = fast_rcnn_losses(t("frcnn_logits"), dl4, t("frcnn_gt_classes"), t("frcnn_props"), t("frcnn_gt_boxes"))
+    assert abs(float(ls["loss_box_reg"]) - want[1]) <= 1e-5 * want[1]
