@@ -486,7 +486,7 @@ def main():
             ops.GEMM_EVENTS = None
         eng.use_cuda_graph = use_graph
         traffic = None   # DRAM bytes per dense launch from the committed ncu capture of the same step (profiles/)
-        tname = "r01_gemm_step_metrics_chain.json" if eng.use_chain else "r01_gemm_step_metrics.json"
+        tname = "r01_gemm_step_metrics_final.json" if eng.use_chain else "r01_gemm_step_metrics.json"
         tp = os.path.join(ROOT, "profiles", tname)
         l2_bytes = None
         if os.path.exists(tp):
@@ -495,8 +495,8 @@ def main():
         alg_tflop = algorithmic_gflop_per_image(cfg) * BATCH / 1e3
         ach = alg_tflop / (gemm_ms / 1e3)
         roof = {"bound": "tensor",
-                "kernel": "gemm_chain_kernel (res3-res5: one persistent layer-chain launch per stage) + gemm_bf16_tc_kernel (stem, res2, FPN, "
-                          "RPN head, box head): all dense layers of the step" if eng.use_chain else
+                "kernel": "gemm_chain_kernel (res3-res5: one persistent layer-chain launch per stage) + gemm_bf16_tc_kernel / gemm_bf16_tc2_kernel "
+                          "(stem, res2, FPN, RPN head, box head; 2-CTA tiles on the long-K layers): all dense layers of the step" if eng.use_chain else
                           "gemm_bf16_tc_kernel (all dense layers: 104 backbone convs, FPN, RPN head, box head)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "traffic_note": f"mean dram__bytes_read+write per dense launch over the {n_gemm} launches of one step (ncu, profiles/{tname})",
