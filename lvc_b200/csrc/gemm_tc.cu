@@ -63,7 +63,10 @@ __host__ __device__ inline int gemm_smem_bytes(int block_n, int mode, int num_st
 
 // KIND 0: bf16 operands (kind::f16); KIND 1: fp32 operands as tf32 (kind::tf32).  UPS 1: the epilogue adds the 2x-upsampled coarser FPN
 // level (its own instantiation: the other layers' code is untouched).
-template <int BLOCK_N, int MODE, int KIND, int UPS = 0>
+// TAP3 1 (3x3 convs on narrow tiles): the three kw taps of a kernel row read ONE [136 x 64] A tile through row-shifted descriptors
+// (tools/desc_probe.cu: exact for any 128-byte row offset inside a SWIZZLE_128B tile); a stage = that A tile + the three taps' B tiles.
+constexpr int kTap3BytesA = 136 * 128;   // 17 KB: rows m0 + shift(kh, kw = 0) .. + 135 cover the 130 rows the three taps touch
+template <int BLOCK_N, int MODE, int KIND, int UPS = 0, int TAP3 = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -72,9 +75,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024-byte alignment
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int kA = TAP3 ? kTap3BytesA : kStageBytesA;
+  constexpr int kB = TAP3 ? 3 * Cfg::kStageBytesB : Cfg::kStageBytesB;
   const uint32_t smem_a0 = smem_base;
-  const uint32_t smem_b0 = smem_base + kStages * kStageBytesA;
-  const uint32_t off_staging = kStages * Cfg::kStageBytes;
+  const uint32_t smem_b0 = smem_base + kStages * kA;
+  const uint32_t off_staging = kStages * (kA + kB);
   const uint32_t staging_bytes = (MODE == 1) ? 2u * BLOCK_M * p.phase_cols * 2u : 0u;
   const uint32_t off_ident = off_staging + staging_bytes;
   const uint32_t off_ctrl = off_ident + (p.has_res ? kIdentBytes : 0);
@@ -130,6 +135,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const bool has_res = p.has_res != 0, no_tma = (p.debug & 2) != 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+        if constexpr (TAP3) {
+          for (int kh = 0; kh < 3; kh++) {
+            const int row = m0 + p.shift[3 * kh];             // the kw = 0 tap; kw = 1, 2 are the next two rows of the same tile
+            for (int kb = 0; kb < k_blocks; kb++) {
+              const uint32_t fb = bar_full + 8 * stage;
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+              mbar_arrive_expect_tx(fb, kA + kB);
+              tma_load_2d(smem_a0 + stage * kA, &tmap_a, fb, kb * k_elems, row);
+#pragma unroll
+              for (int kw = 0; kw < 3; kw++)
+                tma_load_2d(smem_b0 + stage * kB + kw * Cfg::kStageBytesB, &tmap_w, fb, (3 * kh + kw) * Kdim + kb * k_elems, n0);
+              if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+          continue;
+        }
         for (int t = 0; t < taps; t++) {
           const int row = m0 + p.shift[t];
           const int wcol0 = t * Kdim;
@@ -178,6 +199,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n_rem = Ndim - n0;
         const int n_eff = n_rem >= BLOCK_N ? BLOCK_N : ((n_rem + 15) & ~15);
         const uint32_t idesc_t = (idesc & ~(0x3fu << 17)) | ((uint32_t)(n_eff >> 3) << 17);
+        if constexpr (TAP3) {
+          const int groups = 3 * p.k_blocks;                  // (kh, kb) groups of three taps
+          for (int gi = 0; gi < groups; gi++) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t adesc = adesc0 + (uint64_t)(stage * (kA >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kB >> 4));
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++)
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; k++)      // A rows shifted by kw: + kw * 128 bytes = + 8 * kw in the (address >> 4) field
+                umma_bf16(tmem_d, adesc + 8 * kw + 2 * k, bdesc + (uint64_t)(kw * (Cfg::kStageBytesB >> 4)) + 2 * k, idesc_t,
+                          (gi > 0 || kw > 0 || k > 0) ? 1u : 0u);
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(bar_tfull + 8 * b);
+          continue;
+        }
         for (int ki = 0; ki < k_iters; ki++) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -380,10 +420,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 8 * j + 4);
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
                 [[maybe_unused]] uint4 ut = make_uint4(0, 0, 0, 0);
                 if constexpr (UPS) { if (up_row != nullptr) ut = __ldg(reinterpret_cast<const uint4*>(up_row + c + 8 * j)); }
                 [[maybe_unused]] const uint32_t* uw = &ut.x;
+#pragma unroll
                 for (int e = 0; e < 4; e++) {
                   float a0 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e]) + bb[2 * e];
                   float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
@@ -674,15 +714,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 }
 
 
-template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0>
+template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0, int TAP3 = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
                        cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res);
+  const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res) +
+                   (TAP3 ? p.num_stages * (kTap3BytesA - kStageBytesA + 2 * BLOCK_N * BLOCK_K * 2) : 0);
   if (smem > 232448) return set_error(LVCB200_EINVAL, "gemm: internal shared-memory budget exceeded");
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
@@ -697,9 +738,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS>, ta, tw, td, tr, p));
+    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3>, ta, tw, td, tr, p));
   } else {
-    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   }
   return check_launch("gemm_bf16_tc_kernel");
 }
@@ -851,6 +892,23 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
     }
   }
   if (p.up) return launch_gemm<256, 1, 0, 1>(ta, tw, td, tr, p, s);
+  {  // 3x3 conv on a 64-wide tile (res2 conv2): the three kw taps share one A tile (TAP3 instantiation)
+    static const char* e_t3 = getenv("LVCB200_GEMM_TAP3");
+    bool tap3 = (e_t3 == nullptr || atoi(e_t3) != 0) && d->taps == 9 && bn == 64 && mode == 1 && !tf32 && !p.has_res && !p.warp_epi;
+    for (int kh = 0; kh < 3 && tap3; kh++)
+      tap3 = d->shift[3 * kh + 1] == d->shift[3 * kh] + 1 && d->shift[3 * kh + 2] == d->shift[3 * kh] + 2;
+    if (tap3) {
+      GemmParams p3 = p;
+      const int stage3 = kTap3BytesA + 3 * 64 * BLOCK_K * 2;
+      p3.num_stages = (232448 - (kCtrlBytes + 1024) - 2 * BLOCK_M * p3.phase_cols * 2) / stage3;
+      if (p3.num_stages > kMaxStages) p3.num_stages = kMaxStages;
+      if (p3.num_stages >= 2) {
+        CUtensorMap ta136;
+        if ((rc = make_tmap_2d(&ta136, d->A, d->M_rows, d->K, d->lda, 136))) return rc;
+        return launch_gemm<64, 1, 0, 0, 1>(ta136, tw, td, tr, p3, s);
+      }
+    }
+  }
   const CUtensorMap& tdu = p.warp_epi ? td32 : td;
   if (tf32) return bn == 256 ? launch_gemm<256, 1, 1>(ta, tw, tdu, tr, p, s) : launch_gemm<128, 1, 1>(ta, tw, tdu, tr, p, s);
   switch (bn) {
