@@ -894,7 +894,8 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   if (p.up) return launch_gemm<256, 1, 0, 1>(ta, tw, td, tr, p, s);
   {  // 3x3 conv on a 64-wide tile (res2 conv2): the three kw taps share one A tile (TAP3 instantiation)
     static const char* e_t3 = getenv("LVCB200_GEMM_TAP3");
-    bool tap3 = (e_t3 == nullptr || atoi(e_t3) != 0) && d->taps == 9 && bn == 64 && mode == 1 && !tf32 && !p.has_res && !p.warp_epi;
+    bool tap3 = (e_t3 == nullptr || atoi(e_t3) != 0) && d->taps == 9 && bn == 64 && mode == 1 && !tf32 && !p.has_res && !p.warp_epi &&
+                d->M >= 4096 && d->M_rows >= 136;   // small planes gain nothing and the 136-row TMA box needs that many rows
     for (int kh = 0; kh < 3 && tap3; kh++)
       tap3 = d->shift[3 * kh + 1] == d->shift[3 * kh] + 1 && d->shift[3 * kh + 2] == d->shift[3 * kh] + 2;
     if (tap3) {

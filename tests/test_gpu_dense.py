@@ -65,7 +65,8 @@ def _conv_weight_to_gemm(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
-@pytest.mark.parametrize("n,H,W,Cin,Cout", [(2, 25, 42, 128, 256), (1, 50, 84, 256, 256), (3, 13, 21, 64, 64), (2, 16, 16, 512, 512)])
+@pytest.mark.parametrize("n,H,W,Cin,Cout", [(2, 25, 42, 128, 256), (1, 50, 84, 256, 256), (3, 13, 21, 64, 64), (2, 16, 16, 512, 512),
+                                                 (2, 50, 84, 64, 64), (2, 40, 60, 128, 64)])   # the last two take the TAP3 path (shared A tile)
 def test_conv3x3_as_shift_gemm(n, H, W, Cin, Cout):
     g = torch.Generator(device="cpu").manual_seed(H * W)
     x = torch.randn(n, Cin, H, W, generator=g).bfloat16().to(DEV)
