@@ -384,7 +384,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / warnings go to stderr: stdout carries exactly one JSON line
+        # NCCL writes its version banner straight to file descriptor 1 of every rank; point fd 1 at stderr for the run and restore it
+        # for the one JSON line rank 0 prints
+        sys.stdout.flush()
+        _saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(args.warmup, 3)
     K = args.steps
@@ -551,7 +555,12 @@ def main():
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, sd)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if world > 1:
+            os.dup2(_saved_stdout_fd, 1)       # the real stdout back, for the one JSON line
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
