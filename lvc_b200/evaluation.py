@@ -105,6 +105,18 @@ class COCOResultCollector(DatasetEvaluator):
         return {"num_images": len(preds), "num_detections": len(results), "results": results}
 
 
+def inference_shard(n, rank=None, world_size=None):
+    """The reference's InferenceSampler rule (detectron2/data/samplers/distributed_sampler.py:191-194): rank r of W takes the
+    contiguous block [r * ceil(n / W), min((r + 1) * ceil(n / W), n)) -- so that chain(*gather(...)) on rank 0 is in dataset order.
+    Images shard with NO data-path collective; only the results are gathered."""
+    if rank is None or world_size is None:
+        on = dist.is_available() and dist.is_initialized()
+        rank, world_size = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    per = (n - 1) // world_size + 1 if n > 0 else 0
+    begin = per * rank
+    return range(min(begin, n), min(begin + per, n))
+
+
 def inference_on_dataset(model, data_loader, evaluator):
     """Same contract as the reference's ``inference_on_dataset``: runs ``model`` over ``data_loader`` (an iterable with a
     length, yielding list[dict] batches), feeds every (inputs, outputs) pair to ``evaluator.process`` and returns

@@ -51,3 +51,38 @@ def test_driver_protocol_and_result_file(tmp_path):
     assert on_disk[0]["bbox"] == pytest.approx(want["bbox"]) and on_disk[0]["category_id"] == want["category_id"] + 1
     w = on_disk[0]["bbox"]
     assert w[2] > 0 and w[3] > 0      # XYWH
+
+
+# ---------------------------------------------------------------- N > 1: images shard, results gather (gloo, world size 2, CPU)
+class _StubModel:
+    """Stands in for GeneralizedRCNN: one deterministic Instances per image id."""
+
+    def __call__(self, batch):
+        return [{"instances": _inst(1 + x["image_id"] % 3, seed=x["image_id"])} for x in batch]
+
+
+def _shard_worker(rank, world, port, n_images, ret):
+    import torch.distributed as dist
+    from lvc_b200.evaluation import inference_shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = inference_shard(n_images)
+    batches = [[{"image_id": i} for i in list(mine)[j:j + 2]] for j in range(0, len(mine), 2)]
+    out = inference_on_dataset(_StubModel(), batches, COCOResultCollector())
+    ret[rank] = (list(mine), out.get("num_images"), [r["image_id"] for r in out.get("results", [])])
+    dist.destroy_process_group()
+
+
+def test_sharded_mining_gathers_in_dataset_order_gloo_world2():
+    import torch.multiprocessing as mp
+    from lvc_b200.evaluation import inference_shard
+    assert [list(inference_shard(7, r, 2)) for r in (0, 1)] == [[0, 1, 2, 3], [4, 5, 6]]          # contiguous ceil(n / W) blocks
+    assert [list(inference_shard(5, r, 8)) for r in range(8)] == [[0], [1], [2], [3], [4], [], [], []]
+    assert list(inference_shard(0, 0, 2)) == []
+    port = 29500 + (os.getpid() % 2000) + 7
+    ret = mp.Manager().dict()
+    mp.spawn(_shard_worker, args=(2, port, 7, ret), nprocs=2, join=True)
+    assert ret[0][0] == [0, 1, 2, 3] and ret[1][0] == [4, 5, 6]
+    assert ret[1][1] is None                                              # only rank 0 holds the gathered results
+    want = [i for i in range(7) for _ in range(1 + i % 3)]               # every detection, in dataset order
+    assert ret[0][1] == 7 and ret[0][2] == want
