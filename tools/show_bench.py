@@ -1,6 +1,9 @@
 """Print the key numbers of a bench.py JSON line."""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)   # `| head` closes the pipe early
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(f"value {d['value']:.1f} {d['unit']}  ({d['ms_per_step']:.3f} ms/step, n_gpus {d['n_gpus']});  e2e {d['e2e']['value']:.1f} ({d['e2e']['ms_per_step']:.3f} ms)")
