@@ -83,3 +83,18 @@ def test_gemm_chain_host_validation():
     assert lib.lvcb200_gemm_chain_workspace((_lib.GemmDesc * 1)(f32), 1) == 0
     plan = _lib.ChainPlan()
     assert lib.lvcb200_gemm_chain_run(ctypes.byref(plan), None) == -1      # empty plan refused
+
+
+def test_match_boxes_host_validation():
+    """Matcher arguments are checked on the host (matcher.py:46-57 asserts) before any CUDA call."""
+    lib = _lib.load()
+    thr = (ctypes.c_float * 2)(0.3, 0.7)
+    lab = (ctypes.c_int8 * 3)(0, -1, 1)
+    assert lib.lvcb200_match_boxes(None, 0, None, None, 0, thr, 2, lab, 1, None, None, None, None, 0, None) == 0      # P == 0: nothing to do
+    bad_thr = (ctypes.c_float * 2)(0.7, 0.3)
+    assert lib.lvcb200_match_boxes(None, 0, None, None, 5, bad_thr, 2, lab, 0, None, None, None, None, 0, None) == -1
+    assert b"sorted" in lib.lvcb200_last_error()
+    bad_lab = (ctypes.c_int8 * 3)(0, 2, 1)
+    assert lib.lvcb200_match_boxes(None, 0, None, None, 5, thr, 2, bad_lab, 0, None, None, None, None, 0, None) == -1
+    assert b"labels" in lib.lvcb200_last_error()
+    assert lib.lvcb200_match_boxes_workspace(20) >= 80
