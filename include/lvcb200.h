@@ -27,7 +27,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define LVCB200_ABI_VERSION 1
+#define LVCB200_ABI_VERSION 2
 #define LVCB200_EINVAL (-1)      /* bad argument (shape, alignment, NULL) */
 #define LVCB200_EWORKSPACE (-2)  /* workspace too small */
 #define LVCB200_EUNSUPPORTED (-3)
@@ -213,6 +213,12 @@ typedef struct {
    * up = the coarser level's zero-bordered bf16 plane [n, up_plane_h, up_plane_w, >= N] (row pitch ldu elements), this plane being
    * exactly twice its interior size.  bf16 output, N % 64 == 0, no residual; added in fp32 before the single bf16 rounding. */
   const void* upsample_add; int64_t ldu; int up_plane_h, up_plane_w;
+  /* optional (appended; 0 = off): STRICT mode -- fp32-grade results on the bf16 tensor pipe (the reference is fp32 end to end,
+   * wrappers.py:94-98).  Every real operand x is a bf16 pair x = hi + lo (hi = bf16(x), lo = bf16(x - hi)).  A, residual and a
+   * bf16 D are pair matrices: hi half at row 0, lo half at row split_rows (a multiple of 128, >= M; M_rows covers both halves);
+   * W is [N, taps * 2K] with [W_hi | W_lo] per tap.  D = A_hi W_hi + A_lo W_hi + A_hi W_lo (+ bias + R_hi + R_lo), fp32
+   * accumulation; a bf16 D is written as a pair, an fp32 D as is.  No upsample_add, not chainable. */
+  int64_t split_rows;
 } lvcb200_gemm_desc;
 
 int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d /*host*/, void* stream);
@@ -251,6 +257,26 @@ int lvcb200_maxpool_s2d(const void* in, int n, int Ho, int Wo, int C, void* out,
 int lvcb200_subsample2(const void* in, int n, int H, int W, int C, void* out, void* stream);
 /* out += nearest-2x-upsample(top)  (FPN top-down path, fpn.py:131-133), zero-bordered bf16 planes. */
 int lvcb200_upsample2_add(const void* top, int n, int Ht, int Wt, int C, void* inout, int H, int W, void* stream);
+
+/* STRICT engine mode helpers (see lvcb200_gemm_desc.split_rows): planes / matrices held as bf16 hi/lo pairs, the lo half
+ * `split_rows` rows after the hi half.  stem_s2d4_pair / maxpool_s2d_pair / upsample2_add_pair are the pair forms of the three
+ * kernels above (arithmetic in fp32 on hi + lo, result re-split); subsample2 is a pure copy and is simply applied to each half.
+ * pair_merge: out[r, c] = hi + lo as fp32 (dense [rows, cols]); pair_split: the inverse.  cols % 8 == 0. */
+int lvcb200_stem_s2d4_pair(const void* const* images, int image_dtype, const int32_t* image_sizes, int n, int Hpad, int Wpad,
+                           const float* mean, const float* inv_std, void* out, int64_t split_rows, void* stream);
+int lvcb200_maxpool_s2d_pair(const void* in, int64_t in_split_rows, int n, int Ho, int Wo, int C, void* out, int64_t out_split_rows,
+                             void* stream);
+int lvcb200_upsample2_add_pair(const void* top, int64_t top_split_rows, int n, int Ht, int Wt, int C, void* inout,
+                               int64_t io_split_rows, int H, int W, void* stream);
+int lvcb200_pair_merge(const void* pair, int64_t split_rows, int64_t rows, int cols, float* out, void* stream);
+int lvcb200_pair_split(const float* in, int64_t rows, int cols, void* pair, int64_t split_rows, void* stream);
+/* out[r] = scale / (||x_r||_2 + eps), the per-row factor of CosineSimOutputLayers.forward (lvc/modeling/roi_heads/fast_rcnn.py:826-829).
+ * x [R, C] row pitch ld: LVCB200_BF16 (lo_off != 0: a bf16 pair, lo element = hi element + lo_off) or LVCB200_F32. */
+int lvcb200_row_inv_norm(const void* x, int dtype, int64_t lo_off, int64_t R, int C, int64_t ld, float scale, float eps, float* out,
+                         void* stream);
+/* convert_boxes_to_pooler_format (detectron2/modeling/poolers.py:69-96) on the RPN's padded output: proposals [n, P, 4] + counts [n]
+ * -> rois [n*P, 5] = (image, x1, y1, x2, y2), roi_image [n*P] int32 (image index, -1 for padding rows). */
+int lvcb200_make_rois(const float* proposals, const int32_t* counts, int n, int P, float* rois, int32_t* roi_image, void* stream);
 
 /* "Next" row: crop front end of the kNN descriptors.  Replaces get_crops_qe (lvc/data/utils.py:485-519) +
  * preprocess_crops (tools/run_nearest_neighbours.py:102-105): image = planar [3,H,W] uint8 or fp32 on the device;

@@ -10,6 +10,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LVCB200_LIB") or os.path.join(_HERE, "liblvcb200.so")   # LVCB200_LIB: A/B another build on the same box
 
+ABI_VERSION = 2
 F32, BF16, U8, F16 = 0, 1, 2, 3
 OUT_NCHW, OUT_NHWC = 0, 1
 
@@ -42,7 +43,8 @@ class GemmDesc(Structure):
                 ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64), ("D", c_void_p), ("ldd", c_int64),
                 ("d_dtype", c_int), ("M", c_int64), ("N", c_int), ("K", c_int), ("taps", c_int), ("shift", c_int32 * 9),
                 ("relu", c_int), ("plane_h", c_int), ("plane_w", c_int),
-                ("upsample_add", c_void_p), ("ldu", c_int64), ("up_plane_h", c_int), ("up_plane_w", c_int)]
+                ("upsample_add", c_void_p), ("ldu", c_int64), ("up_plane_h", c_int), ("up_plane_w", c_int),
+                ("split_rows", c_int64)]
 
 
 class ChainPlan(Structure):
@@ -96,6 +98,13 @@ _SIGS = {
     "lvcb200_crops_qe": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_subsample2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_upsample2_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "lvcb200_stem_s2d4_pair": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "lvcb200_maxpool_s2d_pair": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "lvcb200_upsample2_add_pair": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "lvcb200_pair_merge": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "lvcb200_pair_split": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "lvcb200_row_inv_norm": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "lvcb200_make_rois": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -117,7 +126,7 @@ def load():
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.lvcb200_abi_version() != 1:
+        if lib.lvcb200_abi_version() != ABI_VERSION:
             raise LvcB200Error("liblvcb200.so ABI version mismatch")
         _lib = lib
     return _lib

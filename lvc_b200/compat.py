@@ -21,11 +21,30 @@ _SITES = {
 }
 
 
-def install(strict: bool = False):
-    """Rebind the reference's operator names to lvc_b200.layers.  Returns the list of (module, name) pairs patched.
-    Modules that are not importable in this environment are skipped unless ``strict``."""
+_saved = []   # (module or registry map, name, previous object) for uninstall()
+
+
+def install(strict: bool = False, architectures: bool = True):
+    """Rebind the reference's operator names to lvc_b200.layers and (``architectures``) re-register the mining-path
+    meta-architectures -- ``GeneralizedRCNN``, ``GeneralizedRCNNRegOnly``, ``ProposalNetwork`` -- in the reference's
+    ``META_ARCH_REGISTRY`` (lvc/modeling/meta_arch/build.py:3-17), so that ``lvc.modeling.build_model(cfg)`` -- and with it
+    ``tools/train_net.py --eval-only`` / ``tools/train_net_reg_qe.py --eval-only`` -- constructs the B200 models by name.
+    Returns the list of (module, name) pairs patched.  Modules that are not importable in this environment are skipped unless
+    ``strict``."""
     from . import layers
     patched = []
+    if architectures:
+        try:
+            build = sys.modules.get("lvc.modeling.meta_arch.build") or importlib.import_module("lvc.modeling.meta_arch.build")
+            from .modeling import META_ARCHITECTURES
+            omap = build.META_ARCH_REGISTRY._obj_map      # Registry.register() refuses to overwrite; the map is the registry
+            for name, cls in META_ARCHITECTURES.items():
+                _saved.append((omap, name, omap.get(name)))
+                omap[name] = cls
+                patched.append(("lvc.modeling.meta_arch.build.META_ARCH_REGISTRY", name))
+        except Exception:
+            if strict:
+                raise
     for name, mods in _SITES.items():
         impl = getattr(layers, name)
         for m in mods:
@@ -36,6 +55,7 @@ def install(strict: bool = False):
                     raise
                 continue
             if hasattr(mod, name):
+                _saved.append((mod, name, getattr(mod, name)))
                 setattr(mod, name, impl)
                 patched.append((m, name))
     try:   # tools/run_nearest_neighbours.py:142-162, 214-227
@@ -43,9 +63,23 @@ def install(strict: bool = False):
         if tool is not None:
             from . import knn
             for name in ("assemble_tensors", "run_nearest_neighbours", "get_nn_class_confirmatory"):
+                _saved.append((tool, name, getattr(tool, name)))
                 setattr(tool, name, getattr(knn, name))
                 patched.append(("tools.run_nearest_neighbours", name))
     except Exception:
         if strict:
             raise
     return patched
+
+
+def uninstall():
+    """Undo install(): put the reference's own objects back (most recent first)."""
+    while _saved:
+        holder, name, prev = _saved.pop()
+        if isinstance(holder, dict):
+            if prev is None:
+                holder.pop(name, None)
+            else:
+                holder[name] = prev
+        else:
+            setattr(holder, name, prev)

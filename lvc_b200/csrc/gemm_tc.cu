@@ -36,6 +36,7 @@ struct GemmParams {
   const __nv_bfloat16* up; long long ldu; int up_ph, up_pw;   // UPS instantiation: D += nearest-2x-upsample(up) (FPN top-down add)
   int warp_epi;                    // MODE 1: warp-private staging + one TMA store per warp per 64 columns (no CTA-wide barriers)
   int debug;                       // experiments only, bit mask: 1 = issue no MMAs, 2 = issue no TMA loads, 4 = issue no TMA stores (results are garbage)
+  int split_rows;                  // SPLIT instantiations: row offset of the lo half of every hi/lo bf16 pair matrix (A, residual, D)
 };
 
 // MODE 0: epilogue stores straight from registers (fp32 heads, tiny N).
@@ -66,7 +67,12 @@ __host__ __device__ inline int gemm_smem_bytes(int block_n, int mode, int num_st
 // TAP3 1 (3x3 convs on narrow tiles): the three kw taps of a kernel row read ONE [136 x 64] A tile through row-shifted descriptors
 // (tools/desc_probe.cu: exact for any 128-byte row offset inside a SWIZZLE_128B tile); a stage = that A tile + the three taps' B tiles.
 constexpr int kTap3BytesA = 136 * 128;   // 17 KB: rows m0 + shift(kh, kw = 0) .. + 135 cover the 130 rows the three taps touch
-template <int BLOCK_N, int MODE, int KIND, int UPS = 0, int TAP3 = 0>
+// SPLIT 1 (strict engine mode, fp32-grade results on the bf16 tensor pipe): every real operand x is carried as a bf16 pair
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi): 16 significant bits, |x - hi - lo| <= 2^-18 |x|).  A, the residual and a bf16 D are
+// [2 * split_rows, cols] matrices with the hi half at row 0 and the lo half at row split_rows; W is [N, taps * 2K] with [hi | lo]
+// per tap.  The contraction is the classic three-term product A_hi W_hi + A_lo W_hi + A_hi W_lo (the dropped lo * lo term is
+// 2^-18 relative), all accumulated in the same fp32 TMEM tile: three K loops per tap instead of one.
+template <int BLOCK_N, int MODE, int KIND, int UPS = 0, int TAP3 = 0, int SPLIT = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -124,7 +130,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int k_iters = p.taps * p.k_blocks;
+  const int k_iters = p.taps * p.k_blocks * (SPLIT ? 3 : 1);
+  constexpr int kSplitPasses = SPLIT ? 2 : 1;        // residual / output halves
 
   if (warp == 0) {
     if (lane == 0) {  // ===================================== TMA producer
@@ -152,30 +159,36 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           continue;
         }
         for (int t = 0; t < taps; t++) {
-          const int row = m0 + p.shift[t];
-          const int wcol0 = t * Kdim;
-          for (int kb = 0; kb < k_blocks; kb++) {
-            const uint32_t fb = bar_full + 8 * stage;
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            if (no_tma) { mbar_arrive(fb); }
-            else {
-              mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
-              tma_load_2d(smem_a0 + stage * kStageBytesA, &tmap_a, fb, kb * k_elems, row);
-              tma_load_2d(smem_b0 + stage * Cfg::kStageBytesB, &tmap_w, fb, wcol0 + kb * k_elems, n0);
+#pragma unroll 1
+          for (int sp = 0; sp < (SPLIT ? 3 : 1); sp++) {   // SPLIT: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
+            const int row = m0 + p.shift[t] + ((SPLIT && sp == 1) ? p.split_rows : 0);
+            const int wcol0 = SPLIT ? (2 * t + (sp == 2 ? 1 : 0)) * Kdim : t * Kdim;
+            for (int kb = 0; kb < k_blocks; kb++) {
+              const uint32_t fb = bar_full + 8 * stage;
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+              if (no_tma) { mbar_arrive(fb); }
+              else {
+                mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                tma_load_2d(smem_a0 + stage * kStageBytesA, &tmap_a, fb, kb * k_elems, row);
+                tma_load_2d(smem_b0 + stage * Cfg::kStageBytesB, &tmap_w, fb, wcol0 + kb * k_elems, n0);
+              }
+              if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
             }
-            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
           }
         }
         if (has_res) {   // residual [128 x 64] tiles as extra A operands; a stage carries two of them (A slot + B slot)
           constexpr int kResPerStage = (BLOCK_N >= 128) ? 2 : 1;
-          for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j += kResPerStage) {
-            const uint32_t fb = bar_full + 8 * stage;
-            const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < Ndim);
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            mbar_arrive_expect_tx(fb, two ? 2 * kStageBytesA : kStageBytesA);
-            tma_load_2d(smem_a0 + stage * kStageBytesA, &tmap_r, fb, n0 + j * 64, m0);
-            if (two) tma_load_2d(smem_b0 + stage * Cfg::kStageBytesB, &tmap_r, fb, n0 + (j + 1) * 64, m0);
-            if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+          for (int hp = 0; hp < kSplitPasses; hp++) {      // SPLIT: the hi tiles, then the lo tiles
+            const int rrow = m0 + (SPLIT ? hp * p.split_rows : 0);
+            for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j += kResPerStage) {
+              const uint32_t fb = bar_full + 8 * stage;
+              const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < Ndim);
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+              mbar_arrive_expect_tx(fb, two ? 2 * kStageBytesA : kStageBytesA);
+              tma_load_2d(smem_a0 + stage * kStageBytesA, &tmap_r, fb, n0 + j * 64, rrow);
+              if (two) tma_load_2d(smem_b0 + stage * Cfg::kStageBytesB, &tmap_r, fb, n0 + (j + 1) * 64, rrow);
+              if (++stage == (uint32_t)kStages) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -236,6 +249,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (has_res) {
           if constexpr (BLOCK_N >= 64) {
             constexpr int kResPerStage = (BLOCK_N >= 128) ? 2 : 1;
+            for (int hp = 0; hp < kSplitPasses; hp++)
             for (int j = 0; j < BLOCK_N / 64 && n0 + j * 64 < Ndim; j += kResPerStage) {
               const bool two = kResPerStage == 2 && (n0 + (j + 1) * 64 < Ndim);
               mbar_wait(bar_full + 8 * stage, phase);
@@ -396,7 +410,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int sw = r & 7;                           // SWIZZLE_128B: 16-byte chunk index ^= row & 7
         const int cols_per_warp = p.phase_cols >> 1;    // 32 (phase 64) or 64 (phase 128)
 #pragma unroll 1
-        for (int pc = 0; pc < BLOCK_N; pc += p.phase_cols) {
+        for (int pcs = 0; pcs < BLOCK_N * kSplitPasses; pcs += p.phase_cols) {
+          // SPLIT: every phase runs twice -- first the hi half bf16(v), then the lo half bf16(v - hi), stored split_rows further down
+          const int pc = SPLIT ? (pcs / (2 * p.phase_cols)) * p.phase_cols : pcs;
+          [[maybe_unused]] const bool lo_pass = SPLIT && ((pcs / p.phase_cols) & 1);
           if (n0 + pc >= p.N) break;
           const uint32_t buf_off = off_staging + (gphase & 1u) * (BLOCK_M * p.phase_cols * 2);
           if (et == 0) tma_store_wait_read<1>();        // the TMA store issued two phases ago (this buffer) has read its smem
@@ -430,7 +447,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   if constexpr (UPS) { a0 += __uint_as_float(uw[e] << 16); a1 += __uint_as_float(uw[e] & 0xffff0000u); }
                   if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
                   if (zero_row) { a0 = 0.f; a1 = 0.f; }
-                  if (p.d_f16) { __half2 hh = __floats2half2_rn(a0, a1); ho[e] = *reinterpret_cast<__nv_bfloat162*>(&hh); }
+                  if constexpr (SPLIT) {
+                    const __nv_bfloat162 hi2 = __floats2bfloat162_rn(a0, a1);
+                    if (lo_pass) {   // v - hi is exact in fp32 (hi holds the leading bits of v)
+                      const float2 hf = __bfloat1622float2(hi2);
+                      ho[e] = __floats2bfloat162_rn(__fsub_rn(a0, hf.x), __fsub_rn(a1, hf.y));
+                    } else ho[e] = hi2;
+                  } else if (p.d_f16) { __half2 hh = __floats2half2_rn(a0, a1); ho[e] = *reinterpret_cast<__nv_bfloat162*>(&hh); }
                   else ho[e] = __floats2bfloat162_rn(a0, a1);
                 }
                 *reinterpret_cast<uint4*>(rowp + (((hs * 4 + j) ^ sw) << 4)) = o;
@@ -440,8 +463,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           fence_proxy_async();                          // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (et == 0) {
+            const int srow = m0 + (lo_pass ? p.split_rows : 0);
             for (int c = pc; c < pc + p.phase_cols && n0 + c < p.N; c += 64)   // rows >= M / cols >= N are clipped by the TMA unit
-              tma_store_2d(&tmap_d, smem_base + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128), n0 + c, m0);
+              tma_store_2d(&tmap_d, smem_base + buf_off + ((c - pc) >> 6) * (BLOCK_M * 128), n0 + c, srow);
             tma_store_commit();
           }
           gphase++;
@@ -714,12 +738,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 }
 
 
-template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0, int TAP3 = 0>
+template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0, int TAP3 = 0, int SPLIT = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
                        cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res) +
@@ -738,9 +762,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3>, ta, tw, td, tr, p));
+    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT>, ta, tw, td, tr, p));
   } else {
-    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   }
   return check_launch("gemm_bf16_tc_kernel");
 }
@@ -770,13 +794,13 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUte
   return check_launch("gemm_bf16_tc2_kernel");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int SPLIT = 0>
 static int launch_gemm_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr,
                             const GemmParams& p, cudaStream_t s) {
   if constexpr (BLOCK_N >= 64) {
-    if (mode == 1) return launch_gemm<BLOCK_N, 1>(ta, tw, td, tr, p, s);
+    if (mode == 1) return launch_gemm<BLOCK_N, 1, 0, 0, 0, SPLIT>(ta, tw, td, tr, p, s);
   }
-  return launch_gemm<BLOCK_N, 0>(ta, tw, td, tr, p, s);
+  return launch_gemm<BLOCK_N, 0, 0, 0, 0, SPLIT>(ta, tw, td, tr, p, s);
 }
 
 }  // namespace lvcb200
@@ -790,6 +814,10 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   LVC_REQUIRE(d->A && d->W && d->D, "gemm: NULL pointer");
   LVC_REQUIRE(d->N % 8 == 0, "gemm: N must be a multiple of 8");
   const bool tf32 = d->a_dtype == LVCB200_F32;   // fp32 operands consumed by the tensor core as TF32
+  const bool split = d->split_rows != 0;         // strict mode: hi/lo bf16 pair operands, three-term product
+  LVC_REQUIRE(!split || (!tf32 && d->split_rows >= d->M && d->split_rows % BLOCK_M == 0 && d->split_rows < (1ll << 30) &&
+                         !d->upsample_add && d->d_dtype != LVCB200_F16 && d->K % BLOCK_K == 0),
+              "gemm: split mode: bf16 pairs, split_rows a multiple of 128 and >= M, K % 64 == 0, no upsample_add, bf16 (pair) or fp32 output");
   LVC_REQUIRE(d->a_dtype == LVCB200_BF16 || tf32, "gemm: a_dtype must be LVCB200_BF16 or LVCB200_F32");
   LVC_REQUIRE(!tf32 || (d->taps == 1 && !d->residual && d->d_dtype != LVCB200_F32 && d->N >= 64), "gemm: tf32 path: single tap, no residual, 16-bit output, N >= 64");
   LVC_REQUIRE(d->K % 8 == 0 && (d->taps == 1 || d->K % BLOCK_K == 0), "gemm: K must be a multiple of 8 (64 when taps > 1)");
@@ -820,7 +848,8 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   p.k_blocks = (d->K + p.k_elems - 1) / p.k_elems;
   p.has_res = d->residual ? 1 : 0;
   // smem split: deep operand pipeline for long K loops, shallow pipeline + wide staging when the epilogue dominates
-  const int k_iters = p.taps * p.k_blocks;
+  const int k_iters = p.taps * p.k_blocks * (split ? 3 : 1);
+  p.split_rows = (int)d->split_rows;
   const int stage_bytes = kStageBytesA + bn * BLOCK_K * 2;
   const bool deep = k_iters >= 12 && !p.has_res;
   if (mode == 1) {
@@ -844,7 +873,7 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   }
   {
     static const char* e_we = getenv("LVCB200_GEMM_WEPI");
-    p.warp_epi = (mode == 1 && !p.up && e_we != nullptr && atoi(e_we) != 0 && ((uintptr_t)d->bias % 16) == 0) ? 1 : 0;   // experiment: same speed as the shared-phase epilogue (profiles/r01_gemm_modes.md)
+    p.warp_epi = (mode == 1 && !p.up && !split && e_we != nullptr && atoi(e_we) != 0 && ((uintptr_t)d->bias % 16) == 0) ? 1 : 0;   // experiment: same speed as the shared-phase epilogue (profiles/r01_gemm_modes.md)
   }
   {  // tuning overrides for experiments (tools/gemm_sweep.py); not used by the engine
     static const char* e_dbg = getenv("LVCB200_GEMM_DEBUG");
@@ -859,14 +888,24 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   CUtensorMap ta, tw, td, tr;
   int rc = make_tmap_2d(&ta, d->A, d->M_rows, d->K, d->lda, BLOCK_M, tf32);
   if (rc) return rc;
-  rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K, d->ldw, bn, tf32);
+  rc = make_tmap_2d(&tw, d->W, d->N, (long long)d->taps * d->K * (split ? 2 : 1), d->ldw, bn, tf32);
   if (rc) return rc;
   td = ta; tr = ta;  // placeholders when unused (a valid map must still be passed by value)
-  if (mode == 1 && (rc = make_tmap_2d(&td, d->D, d->M, d->N, d->ldd, BLOCK_M))) return rc;
+  const long long rows_d = split ? d->split_rows + d->M : d->M;   // a pair matrix ends M rows into its lo half
+  if (mode == 1 && (rc = make_tmap_2d(&td, d->D, rows_d, d->N, d->ldd, BLOCK_M))) return rc;
   CUtensorMap td32 = td;   // [32 x 64] store box of the warp-private epilogue
   if (mode == 1 && p.warp_epi && (rc = make_tmap_2d(&td32, d->D, d->M, d->N, d->ldd, 32))) return rc;
-  if (p.has_res && (rc = make_tmap_2d(&tr, d->residual, d->M, d->N, d->ldr, BLOCK_M))) return rc;
+  if (p.has_res && (rc = make_tmap_2d(&tr, d->residual, rows_d, d->N, d->ldr, BLOCK_M))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if (split) {   // per-layer launches of the SPLIT instantiations (no 2-CTA / TAP3 / chain variants in strict mode)
+    switch (bn) {
+      case 256: return launch_gemm_mode<256, 1>(mode, ta, tw, td, tr, p, s);
+      case 128: return launch_gemm_mode<128, 1>(mode, ta, tw, td, tr, p, s);
+      case 64: return launch_gemm_mode<64, 1>(mode, ta, tw, td, tr, p, s);
+      case 32: return launch_gemm_mode<32, 1>(mode, ta, tw, td, tr, p, s);
+      default: return launch_gemm_mode<16, 1>(mode, ta, tw, td, tr, p, s);
+    }
+  }
   {
     static const char* e_2 = getenv("LVCB200_GEMM_2CTA");
     const int two_cta = e_2 ? atoi(e_2) : 2;   // default: 2-CTA tiles for the big 3x3 convs only (same-box A/B: dense stack -1.7 % sustained)

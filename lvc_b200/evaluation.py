@@ -7,6 +7,7 @@
   the loop is software-pipelined through ``GeneralizedRCNN.inference_stream`` (H2D of batch i+1 overlaps the forward of batch i)
   and there is no per-image ``cuda.synchronize()``; any batch size the loader yields is accepted (the reference pins 1).
 """
+import collections
 import datetime
 import itertools
 import json
@@ -126,12 +127,21 @@ def inference_on_dataset(model, data_loader, evaluator):
     total = len(data_loader)
     logger.info("Start inference on {} batches".format(total))
     evaluator.reset()
-    batches = list(data_loader) if not isinstance(data_loader, (list, tuple)) else data_loader
     start = time.time()
     n_img = 0
-    stream = model.inference_stream(batches) if hasattr(model, "inference_stream") else (model(b) for b in batches)
+    # The loader is consumed LAZILY (the mining path runs over the whole training set: ~100 k images of ~3 MB each): the
+    # pipelined stream pulls one batch ahead, and only the inputs of in-flight batches are remembered here.
+    in_flight = collections.deque()
+
+    def feed():
+        for inputs in data_loader:
+            in_flight.append(inputs)
+            yield inputs
+
+    stream = model.inference_stream(feed()) if hasattr(model, "inference_stream") else (model(b) for b in feed())
     with torch.no_grad():
-        for inputs, outputs in zip(batches, stream):
+        for outputs in stream:
+            inputs = in_flight.popleft()
             evaluator.process(inputs, outputs)
             n_img += len(inputs)
     total_time = time.time() - start

@@ -1,6 +1,8 @@
 from .corrector import BoxCorrectorHead
 from .engine import DetectorEngine
 from .matcher import Matcher, fast_rcnn_losses, pairwise_iou, rpn_losses
-from .rcnn import GeneralizedRCNN
+from .postprocessing import detector_postprocess
+from .rcnn import META_ARCHITECTURES, GeneralizedRCNN, GeneralizedRCNNRegOnly, ProposalNetwork
 
-__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN", "Matcher", "fast_rcnn_losses", "pairwise_iou", "rpn_losses"]
+__all__ = ["BoxCorrectorHead", "DetectorEngine", "GeneralizedRCNN", "GeneralizedRCNNRegOnly", "ProposalNetwork", "META_ARCHITECTURES",
+           "detector_postprocess", "Matcher", "fast_rcnn_losses", "pairwise_iou", "rpn_losses"]

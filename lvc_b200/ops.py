@@ -9,6 +9,8 @@ from . import _lib
 from ._lib import BF16, F32, OUT_NCHW, OUT_NHWC, ChainPlan, DetParams, FMap, GemmDesc, RpnLevel, RpnParams
 
 _ws = {}
+_ws_retired = []     # outgrown scratch buffers stay alive: a captured CUDA graph may still hold their raw pointers
+PLAN_LOG = None      # an engine sets this to a list to learn which layer-chain plans its buffers own (evicted with them)
 GEMM_EVENTS = None   # bench.py sets this to a list to time every GEMM launch with CUDA events on the launch stream
 GEMM_RECORD = None   # bench.py sets this to a list to record every GEMM descriptor of a step (replayed alone inside a CUDA graph)
 
@@ -45,11 +47,11 @@ class gemm_chain:
 
 def _desc_key(d):
     return (d.a_dtype, d.A, d.lda, d.M_rows, d.W, d.ldw, d.bias, d.residual, d.ldr, d.D, d.ldd, d.d_dtype, d.M, d.N, d.K, d.taps,
-            tuple(d.shift), d.relu, d.plane_h, d.plane_w, d.upsample_add)
+            tuple(d.shift), d.relu, d.plane_h, d.plane_w, d.upsample_add, d.split_rows)
 
 
 def chain_eligible(d):
-    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0 and not d.upsample_add
+    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0 and not d.upsample_add and not d.split_rows
 
 
 def run_chain(rec, record=True):
@@ -80,6 +82,8 @@ def run_chain(rec, record=True):
         _lib.check(lib.lvcb200_gemm_chain_plan(arr, n, _lib.ptr(ws), ws.numel(), ctypes.byref(plan)), "lvcb200_gemm_chain_plan")
         ent = (plan, ws, [t for _, t in rec])       # keep the workspace and every operand alive with the plan
         gemm_chain._plans[key] = ent
+        if PLAN_LOG is not None:
+            PLAN_LOG.append(key)
     _lib.check(lib.lvcb200_gemm_chain_run(ctypes.byref(ent[0]), _lib.stream_ptr()), "lvcb200_gemm_chain_run")
 
 
@@ -103,10 +107,21 @@ def flatten_recorded(descs):
     return out
 
 
+def drop_plans(keys):
+    """Forget layer-chain plans (and the operand references they hold) whose buffers are being released."""
+    for k in keys:
+        gemm_chain._plans.pop(k, None)
+
+
 def _workspace(tag, nbytes, device):
+    """Growable scratch per (op, device).  A buffer that is outgrown is RETIRED, not freed: kernels captured into a CUDA
+    graph hold its raw pointer, and returning it to the caching allocator would let a later replay scribble over whatever
+    tensor reuses the block."""
     key = (tag, device.index)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
         buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
@@ -165,6 +180,96 @@ class Plane:
 
     def to_nchw(self):
         return self.valid().permute(0, 3, 1, 2).float().contiguous()
+
+
+class PairPlane(Plane):
+    """Strict-mode plane: x = hi + lo, two bf16 planes in one [2 * split_rows, C] matrix (hi half at row 0, lo half at row
+    split_rows, a multiple of 128 >= n * PH * PW) -- the operand format of the SPLIT GEMM (lvcb200_gemm_desc.split_rows)."""
+
+    def __init__(self, full, n, H, W, C, border=1):
+        PH, PW = H + 2 * border, W + 2 * border
+        M, S = n * PH * PW, full.shape[0] // 2
+        assert full.dim() == 2 and full.shape[1] == C and S >= M and S % 128 == 0
+        super().__init__(full[:M].view(n, PH, PW, C), H, W, C, border)
+        self.full, self.split_rows, self.M = full, S, M
+        self.lo = full[S:S + M].view(n, PH, PW, C)
+
+    @staticmethod
+    def rows_for(n, H, W, border=1):
+        return ((n * (H + 2 * border) * (W + 2 * border) + 127) // 128) * 128
+
+    def to_nchw(self):
+        b = self.border
+        v = self.t[:, b:b + self.H, b:b + self.W].float() + self.lo[:, b:b + self.H, b:b + self.W].float()
+        return v.permute(0, 3, 1, 2).contiguous()
+
+    def merged(self, out=None):
+        """fp32 plane [n, PH, PW, C] = hi + lo (lvcb200_pair_merge)."""
+        if out is None:
+            out = torch.empty(self.t.shape, dtype=torch.float32, device=self.full.device)
+        _lib.check(_lib.load().lvcb200_pair_merge(_lib.ptr(self.full), self.split_rows, self.M, self.C, _lib.ptr(out), _lib.stream_ptr()),
+                   "lvcb200_pair_merge")
+        return out
+
+    @staticmethod
+    def from_nchw(x, border=1):
+        n, c, h, w = x.shape
+        S = PairPlane.rows_for(n, h, w, border)
+        full = torch.zeros((2 * S, c), dtype=torch.bfloat16, device=x.device)
+        p = PairPlane(full, n, h, w, c, border)
+        v = x.permute(0, 2, 3, 1).float()
+        hi = v.bfloat16()
+        p.t[:, border:border + h, border:border + w] = hi
+        p.lo[:, border:border + h, border:border + w] = (v - hi.float()).bfloat16()
+        return p
+
+
+def pair_split(x, out=None):
+    """fp32 [rows, cols] -> bf16 pair matrix [2 * split_rows, cols] (lvcb200_pair_split); returns (full, split_rows)."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    rows, cols = x.shape
+    S = (rows + 127) // 128 * 128
+    if out is None:
+        out = torch.zeros((2 * S, cols), dtype=torch.bfloat16, device=x.device)
+    assert out.shape == (2 * S, cols)
+    _lib.check(_lib.load().lvcb200_pair_split(_lib.ptr(x), rows, cols, _lib.ptr(out), S, _lib.stream_ptr()), "lvcb200_pair_split")
+    return out, S
+
+
+def split_weight(w, taps=1):
+    """fp32 [N, taps*K] -> bf16 [N, taps*2K] with [hi | lo] per tap (W operand of the SPLIT GEMM)."""
+    N = w.shape[0]
+    K = w.shape[1] // taps
+    w = w.float()
+    hi = w.bfloat16()
+    lo = (w - hi.float()).bfloat16()
+    return torch.stack([hi.view(N, taps, K), lo.view(N, taps, K)], dim=2).reshape(N, 2 * taps * K).contiguous()
+
+
+def row_inv_norm(x, scale, eps=1e-5, lo_off=0, rows=None, out=None):
+    """out[r] = scale / (||x_r|| + eps) (CosineSimOutputLayers.forward, fast_rcnn.py:826-829); x bf16 [R, C] (a pair when lo_off != 0) or fp32."""
+    _lib.require_cuda(x)
+    R = rows if rows is not None else x.shape[0]
+    if out is None:
+        out = torch.empty(R, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().lvcb200_row_inv_norm(_lib.ptr(x), _dt(x), lo_off, R, x.shape[1], x.stride(0), scale, eps, _lib.ptr(out),
+                                                _lib.stream_ptr()), "lvcb200_row_inv_norm")
+    return out
+
+
+def make_rois(props, counts, rois=None, roi_image=None):
+    """Padded proposals [n, P, 4] + counts [n] int32 -> pooler-format rois [n*P, 5] and roi_image [n*P] int32 (-1 = padding)."""
+    _lib.require_cuda(props, counts)
+    n, P = props.shape[0], props.shape[1]
+    props = props.contiguous()
+    if rois is None:
+        rois = torch.empty((n * P, 5), dtype=torch.float32, device=props.device)
+    if roi_image is None:
+        roi_image = torch.empty(n * P, dtype=torch.int32, device=props.device)
+    _lib.check(_lib.load().lvcb200_make_rois(_lib.ptr(props), _lib.ptr(counts), n, P, _lib.ptr(rois), _lib.ptr(roi_image), _lib.stream_ptr()),
+               "lvcb200_make_rois")
+    return rois, roi_image
 
 
 def roi_pool_fpn(planes, scales, rois, pooled=7, sampling_ratio=0, out_dtype=torch.float32, out_layout=OUT_NCHW,
@@ -334,17 +439,24 @@ class KnnBank:
 
 # ---------------------------------------------------------------------------------------------- dense
 def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, relu=False, taps=1, shifts=(0,), K=None,
-         M=None, plane_hw=None, upsample_add=None):
+         M=None, plane_hw=None, upsample_add=None, split_rows=0):
     """D = act(sum_t A[m+shift_t, :K] @ W[:, t*K:(t+1)*K]^T + bias + residual).  A [rows, >=K] bf16 (row pitch = stride(0)),
     W [N, taps*K] bf16.  plane_hw=(PH, PW) zeroes border rows of a zero-bordered plane.  upsample_add: a coarser Plane (half the
-    interior size) whose nearest-2x upsampling is added in the epilogue (FPN top-down path, fpn.py:128-134)."""
+    interior size) whose nearest-2x upsampling is added in the epilogue (FPN top-down path, fpn.py:128-134).
+    split_rows != 0 (strict mode): A, residual and a bf16 `out` are hi/lo pair matrices [2 * split_rows, .] (M = rows of one half),
+    W is `split_weight(w, taps)`; three-term bf16 product with fp32-grade accuracy (lvcb200_gemm_desc.split_rows)."""
     _lib.require_cuda(A, W, bias, residual, out)
     assert A.dtype == W.dtype and A.dtype in (torch.bfloat16, torch.float32) and A.stride(1) == 1 and W.stride(1) == 1
     N = W.shape[0]
-    K = K or (W.shape[1] // taps)
+    K = K or (W.shape[1] // (taps * (2 if split_rows else 1)))
+    if split_rows:
+        assert M is not None and split_rows >= M and A.shape[0] >= split_rows + M
     M = M if M is not None else A.shape[0]
     if out is None:
-        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        if split_rows and out_dtype != torch.float32:
+            out = torch.zeros((2 * split_rows, N), dtype=out_dtype, device=A.device)
+        else:
+            out = torch.empty((M, N), dtype=out_dtype, device=A.device)
     assert out.stride(1) == 1
     d = GemmDesc()
     d.a_dtype = _dt(A)
@@ -357,6 +469,7 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
     for i, s in enumerate(shifts):
         d.shift[i] = int(s)
     d.relu = int(relu)
+    d.split_rows = int(split_rows)
     d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
     if upsample_add is not None:
         _lib.require_cuda(upsample_add.t)

@@ -184,7 +184,7 @@ def _images(seed, sizes):
     return ims
 
 
-def gold_e2e(tag, config_rel, depth, sizes, out_sizes, opts=()):
+def gold_e2e(tag, config_rel, depth, sizes, out_sizes, opts=(), seed=100, nfeat=2048, npooled=4096):
     """GeneralizedRCNN.inference (rcnn.py:177-322) end to end with lvc_b200.weights synthetic weights loaded
     strict=True into the reference model."""
     cfg, model = ref_shim.build_reference_model(config_rel, ["MODEL.RESNETS.DEPTH", depth] + list(opts), calibrate=False)
@@ -193,7 +193,7 @@ def gold_e2e(tag, config_rel, depth, sizes, out_sizes, opts=()):
     missing = model.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys, missing.unexpected_keys
     assert all("cell_anchors" in k for k in missing.missing_keys), missing.missing_keys
-    ims = _images(100, sizes)
+    ims = _images(seed, sizes)
     inputs = [{"image": im, "height": oh, "width": ow} for im, (oh, ow) in zip(ims, out_sizes)]
     cap = {}
 
@@ -208,12 +208,12 @@ def gold_e2e(tag, config_rel, depth, sizes, out_sizes, opts=()):
     model.roi_heads.box_predictor.register_forward_hook(hook("pred"))
     with torch.no_grad():
         res = model(inputs)
-    out = dict(sizes=np.array(sizes), out_sizes=np.array(out_sizes), seed=100, depth=depth,
+    out = dict(sizes=np.array(sizes), out_sizes=np.array(out_sizes), seed=seed, depth=depth,
                output_layer=dcfg.output_layer, score_thresh=dcfg.score_thresh_test)
     rng = np.random.default_rng(5)
     for k, v in cap["features"].items():
         flat = v.flatten()
-        idx = rng.integers(0, flat.numel(), 2048)
+        idx = rng.integers(0, flat.numel(), nfeat)
         out[f"feat_{k}_idx"], out[f"feat_{k}_val"] = idx, flat[idx]
         out[f"feat_{k}_absmean"] = v.abs().mean()
     props = cap["proposals"][0]
@@ -221,7 +221,7 @@ def gold_e2e(tag, config_rel, depth, sizes, out_sizes, opts=()):
         out[f"prop_boxes{n}"] = p.proposal_boxes.tensor
         out[f"prop_logits{n}"] = p.objectness_logits
     pooled = cap["pooled"]
-    idx = rng.integers(0, pooled.numel(), 4096)
+    idx = rng.integers(0, pooled.numel(), npooled)
     out["pooled_idx"], out["pooled_val"], out["pooled_shape"] = idx, pooled.flatten()[idx], np.array(pooled.shape)
     out["head_sample"] = cap["head"][:64, :64]
     out["cls_logits_sample"] = cap["pred"][0][:128]
@@ -457,6 +457,10 @@ def main():
         # candidate-sourcing config (CosineSimOutputLayers), R101, one image
         gold_e2e("r101_cosine", "COCO-detection/faster_rcnn_R_50_FPN_ft_all_30shot_aug_ftmore_dropout.yaml", 101,
                  [(256, 320)], [(256, 320)])
+    if "e2e_b8" in which:
+        # BASELINE config #2 itself: R101-FPN candidate-sourcing model, batch 8 of 3x800x1333 (the bench's images: seeds 0..7)
+        gold_e2e("r101_b8", "COCO-detection/faster_rcnn_R_50_FPN_ft_all_30shot_aug_ftmore_dropout.yaml", 101,
+                 [(800, 1333)] * 8, [(800, 1333)] * 8, seed=0, nfeat=32768, npooled=32768)
 
 
 if __name__ == "__main__":

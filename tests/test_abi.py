@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_channel():
     lib = _lib.load()
-    assert lib.lvcb200_abi_version() == 1
+    assert lib.lvcb200_abi_version() == 2
     # argument validation happens on the host before any CUDA call
     rc = lib.lvcb200_gemm_bf16(None, None)
     assert rc == -1 and b"NULL" in lib.lvcb200_last_error()

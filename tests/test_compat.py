@@ -21,3 +21,50 @@ def test_install_patches_reference_import_sites():
     assert pu.batched_nms is layers.batched_nms and fr.batched_nms is layers.batched_nms
     assert sys.modules["detectron2.modeling.poolers"].ROIAlign is layers.ROIAlign
     assert sys.modules["detectron2.layers"].roi_align is layers.roi_align
+    compat.uninstall()
+    assert pu.batched_nms is not layers.batched_nms
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_build_model_returns_b200_architectures_and_state_dicts_interchange():
+    """Registry-level drop-in (lvc/modeling/meta_arch/build.py:3-17): after compat.install() the reference's own build_model(cfg)
+    constructs the lvc_b200 nn.Modules by name, and state dicts move between the reference's modules and ours with strict=True in
+    both directions (same parameter / buffer names and shapes).  The forward itself needs a GPU, which the
+    build container does not have: numerical parity of these models is covered by the -m gpu tests against reference-generated fixtures."""
+    import torch
+    from oracle import ref_shim
+    from lvc_b200 import compat
+    from lvc_b200.modeling import GeneralizedRCNN, GeneralizedRCNNRegOnly, ProposalNetwork
+    cfg, ref = ref_shim.build_reference_model("COCO-detection/faster_rcnn_R_50_FPN_ft_all_30shot_aug_ftmore_dropout.yaml", calibrate=False)
+    compat.install()
+    try:
+        from lvc.modeling import build_model
+        ours = build_model(cfg)
+        assert isinstance(ours, GeneralizedRCNN) and isinstance(ours, torch.nn.Module) and not ours.training
+        assert ours.device == torch.device("cpu") and ours.cfg.output_layer == "CosineSimOutputLayers"
+        ref_sd = ref.state_dict()
+        assert set(ref_sd) == set(ours.state_dict()), set(ref_sd) ^ set(ours.state_dict())
+        assert all(ref_sd[k].shape == v.shape for k, v in ours.state_dict().items())
+        ours.load_state_dict(ref_sd, strict=True)                       # reference checkpoint -> B200 model
+        ref.load_state_dict(ours.state_dict(), strict=True)             # and back
+        assert torch.equal(ours.state_dict()["roi_heads.box_head.fc1.weight"], ref_sd["roi_heads.box_head.fc1.weight"])
+        ours.eval()
+        with pytest.raises(NotImplementedError):
+            ours.train()
+        for arch, cls in (("ProposalNetwork", ProposalNetwork),):
+            c2 = cfg.clone()
+            c2.defrost()
+            c2.MODEL.META_ARCHITECTURE = arch
+            m = build_model(c2)
+            assert isinstance(m, cls)
+        # the box corrector's config (cascade heads, 3 FCs)
+        cfg3, ref3 = ref_shim.build_reference_model("COCO-detection/cascade_ubbr_R_50_FPN_ft_all_30shot_aug_ftmore.yaml",
+                                                    ["QUERY_EXPAND.ENABLED", True, "MODEL.META_ARCHITECTURE", "GeneralizedRCNNRegOnly"],
+                                                    calibrate=False)
+        m3 = build_model(cfg3)
+        assert isinstance(m3, GeneralizedRCNNRegOnly)
+        r3 = ref3.state_dict()
+        assert set(r3) == set(m3.state_dict()), sorted(set(r3) ^ set(m3.state_dict()))[:10]
+        m3.load_state_dict(r3, strict=True)
+    finally:
+        compat.uninstall()
