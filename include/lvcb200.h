@@ -152,6 +152,17 @@ int lvcb200_detections(const float* cls_logits, int64_t logit_pitch, const float
                        float* det_boxes, float* det_scores, int64_t* det_classes, int64_t* det_rows, int32_t* det_counts,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Candidate filter right behind the detector (score mode of get_ret_anns, tools/create_coco_dataset_from_dets_all.py:129-193;
+ * row a15 / f2).  Inputs are lvcb200_detections' outputs (boxes already in output-image coordinates) plus, per image, the
+ * image area height*width as double (pycocotools' float(h)*float(w)), `novel` [num_classes] uint8 (1 = class to mine) and,
+ * optionally, `excluded` [n_images, num_classes] uint8 (1 = this image holds the class's few-shot ground truth, :133-134).
+ * flags [n_images, topk] int8: 1 = pseudo-label candidate (ignore_qe 0), 2 = ignore region (ignore_qe 1; only with full != 0),
+ * 0 = dropped (also every padding slot >= det_counts).  n_keep (optional) [n_images] int32 = number of flags == 1.  topk <= 1024. */
+int lvcb200_candidate_filter(const float* det_boxes, const float* det_scores, const int64_t* det_classes, const int32_t* det_counts,
+                             const double* image_area, int n_images, int topk, int num_classes, const uint8_t* novel,
+                             const uint8_t* excluded, double k_min, double k_max, double ar, int full, int8_t* flags, int32_t* n_keep,
+                             void* stream);
+
 /* Class-agnostic box update of the box corrector.  Replaces BoxOnlyLayersCascade.predict_boxes
  * (lvc/modeling/roi_heads/roi_heads_cascade.py:197-211 -> Box2BoxTransform.apply_deltas, box_regression.py:73-110) followed
  * by Boxes.clip (CascadeROIHeads._create_proposals_from_boxes, cascade_rcnn.py:348-369).  boxes [R,4], deltas [R,>=4] (row pitch
@@ -176,6 +187,12 @@ int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_prepared, vo
 int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
                        const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
                        int64_t* votes, uint8_t* keep, void* stream);
+/* QUERY_EXPAND.COSINE_SIM = False (run_nearest_neighbours.py:154-159): neighbours ranked by -cdist(bank, query) (plain Euclidean
+ * distance, no centring).  Same buffers and outputs as above (top_sim = -distance); exact fp32 SIMT path. */
+int lvcb200_knn_prepare_euclid(const float* bank, int S, int D, void* bank_prepared, void* stream);
+int lvcb200_knn_verify_euclid(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
+                              const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
+                              int64_t* votes, uint8_t* keep, void* stream);
 /* Same contract and the same (exact fp32) results, with the Q x S x D contraction on the tensor cores: TF32 scores straight
  * from the fp32 queries, a rigorous error bound selects a candidate superset per query, candidates are re-scored exactly.
  * Needs 64 <= S <= 4096, D % 8 == 0, and a device workspace of lvcb200_knn_tc_workspace(Q, S) bytes. */

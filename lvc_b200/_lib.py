@@ -76,6 +76,9 @@ _SIGS = {
     "lvcb200_knn_prepare": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_knn_verify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lvcb200_knn_prepare_euclid": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "lvcb200_knn_verify_euclid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "lvcb200_knn_tc_workspace": (c_size_t, [c_int64, c_int]),
     "lvcb200_knn_verify_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -104,6 +107,8 @@ _SIGS = {
     "lvcb200_pair_merge": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "lvcb200_pair_split": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "lvcb200_row_inv_norm": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int64, c_float, c_float, c_void_p, c_void_p]),
+    "lvcb200_candidate_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "lvcb200_make_rois": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 EXPORTS = tuple(_SIGS)

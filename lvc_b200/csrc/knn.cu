@@ -76,15 +76,37 @@ knn_normalize_kernel(const float* __restrict__ bank, int S, int D, const float* 
   if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < 8; i++) t += red2[i]; negc[s] = (float)(-t); }
 }
 
+// Euclidean variant of the bank preparation (QUERY_EXPAND.COSINE_SIM = False, run_nearest_neighbours.py:154-159: ranking by
+// -cdist(bank, query)): no centring, rows kept as they are, bnorm2[s] = |b_s|^2; the verify kernel then scores
+// -sqrt(max(|q|^2 + |b|^2 - 2 q.b, 0)), the matmul form torch.cdist itself uses for more than 25 rows.
+__global__ void __launch_bounds__(256)
+knn_prepare_euclid_kernel(const float* __restrict__ bank, int S, int D, float* __restrict__ mean, float* __restrict__ bhat,
+                          float* __restrict__ bnorm2) {
+  const int s = blockIdx.x;
+  if (s == 0) for (int d = threadIdx.x; d < D; d += blockDim.x) mean[d] = 0.f;
+  __shared__ double red[8];
+  double a = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = s < S ? bank[(size_t)s * D + d] : 0.f;
+    bhat[(size_t)s * D + d] = v;
+    a += (double)v * (double)v;
+  }
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0; for (int i = 0; i < 8; i++) t += red[i]; bnorm2[s] = (float)t; }
+}
+
 __global__ void __launch_bounds__(256)
 knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat, const int64_t* __restrict__ bank_cls, int S, int D,
                   const float* __restrict__ queries, const int64_t* __restrict__ query_cls, int64_t Q, int topk, int knn,
                   int64_t* __restrict__ top_idx, float* __restrict__ top_sim, int64_t* __restrict__ votes, uint8_t* __restrict__ keep,
-                  const uint8_t* __restrict__ only_flagged) {
+                  const uint8_t* __restrict__ only_flagged, const float* __restrict__ bnorm2 = nullptr) {
   __shared__ __align__(16) float As[KT][QT];
   __shared__ __align__(16) float Bs[KT][BT];
   __shared__ float Ss[QT][BT + 1];
   __shared__ float qn[QT];
+  __shared__ float qs2[QT];
   __shared__ float tk_sim[QT][KNN_MAXK];
   __shared__ int tk_idx[QT][KNN_MAXK];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -136,7 +158,7 @@ knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
     if (b0 == 0) {  // finish the query norms: 8 consecutive lanes share a query
       float s = qss;
       s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if ((tid & 7) == 0) { float n = sqrtf(s); qn[lq] = n > 1e-8f ? n : 1e-8f; }
+      if ((tid & 7) == 0) { float n = sqrtf(s); qn[lq] = n > 1e-8f ? n : 1e-8f; qs2[lq] = s; }
       __syncthreads();
     }
 #pragma unroll
@@ -144,7 +166,10 @@ knn_verify_kernel(const float* __restrict__ mean, const float* __restrict__ bhat
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         int r = b0 + tx * 4 + j;
-        Ss[ty * 4 + i][tx * 4 + j] = (r < S) ? __fdiv_rn(acc[i][j], qn[ty * 4 + i]) : -INFINITY;
+        float sc = -INFINITY;
+        if (r < S) sc = bnorm2 == nullptr ? __fdiv_rn(acc[i][j], qn[ty * 4 + i])
+                                          : -sqrtf(fmaxf(__fadd_rn(__fadd_rn(qs2[ty * 4 + i], bnorm2[r]), -2.f * acc[i][j]), 0.f));
+        Ss[ty * 4 + i][tx * 4 + j] = sc;
       }
     __syncthreads();
     if (tid < QT) {  // running top-k, ascending bank index so that ties keep the lower index
@@ -388,6 +413,30 @@ extern "C" int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_p
   if (rc) return rc;
   knn_normalize_kernel<<<knn_s_pad(S), 256, 0, s>>>(bank, S, D, mean, bhat, negc);
   return check_launch("knn_normalize_kernel");
+}
+
+extern "C" int lvcb200_knn_prepare_euclid(const float* bank, int S, int D, void* bank_prepared, void* stream) {
+  LVC_REQUIRE(S >= 1 && D >= 4 && D % 4 == 0, "knn_prepare_euclid: need S >= 1 and D a positive multiple of 4");
+  LVC_REQUIRE(bank && bank_prepared, "knn_prepare_euclid: NULL pointer");
+  float* mean = (float*)bank_prepared;
+  float* bn2 = mean + D;
+  float* bhat = bn2 + knn_s_al(S);
+  knn_prepare_euclid_kernel<<<knn_s_pad(S), 256, 0, (cudaStream_t)stream>>>(bank, S, D, mean, bhat, bn2);
+  return check_launch("knn_prepare_euclid_kernel");
+}
+
+extern "C" int lvcb200_knn_verify_euclid(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
+                                         const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
+                                         int64_t* votes, uint8_t* keep, void* stream) {
+  LVC_REQUIRE(S >= 1 && S <= 4096 && D >= 4 && D % 4 == 0, "knn_verify_euclid: need 1 <= S <= 4096 and D a multiple of 4");
+  LVC_REQUIRE(topk >= 1 && topk <= KNN_MAXK && topk <= S && knn >= 1, "knn_verify_euclid: need 1 <= topk <= min(16, S), knn >= 1");
+  if (Q == 0) return 0;
+  LVC_REQUIRE(bank_prepared && bank_cls && queries && query_cls && top_idx && votes && keep, "knn_verify_euclid: NULL pointer");
+  LVC_REQUIRE(((uintptr_t)queries % 16) == 0, "knn_verify_euclid: queries must be 16-byte aligned");
+  const float* mean = (const float*)bank_prepared;
+  knn_verify_kernel<<<(unsigned)ceil_div64(Q, QT), 256, 0, (cudaStream_t)stream>>>(
+      mean, mean + D + knn_s_al(S), bank_cls, S, D, queries, query_cls, Q, topk, knn, top_idx, top_sim, votes, keep, nullptr, mean + D);
+  return check_launch("knn_verify_kernel<euclid>");
 }
 
 extern "C" int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,

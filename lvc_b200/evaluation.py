@@ -106,6 +106,58 @@ class COCOResultCollector(DatasetEvaluator):
         return {"num_images": len(preds), "num_detections": len(results), "results": results}
 
 
+class CandidateCollector(DatasetEvaluator):
+    """Pseudo-label candidates straight from the detector (rows a15 / f2): consumes results that carry ``candidate_flags``
+    (``model.candidate_filter``, the device-side form of get_ret_anns' score mode) and emits the annotations the reference's
+    offline pass would write (tools/create_coco_dataset_from_dets_all.py:129-238): COCO-result dicts with ``ignore_qe`` /
+    ``iscrowd`` set, ``area`` = w * h and ``id`` = pycocotools ``loadRes``' running index over ALL detections in dataset order
+    (the id the next stage reuses as ``instances.ids``, dataset_mapper.py:383-401).  Ranks gather in rank order
+    (== ``chain(*comm.gather(...))``, coco_evaluation.py:119-126): with ``inference_shard`` that is dataset order."""
+
+    def __init__(self, contiguous_id_to_dataset_id=None):
+        self._map = contiguous_id_to_dataset_id
+        self._records = []
+
+    def reset(self):
+        self._records = []
+
+    def process(self, inputs, outputs):
+        for inp, out in zip(inputs, outputs):
+            inst = out["instances"]
+            n = len(inst)
+            kept = []
+            if n and inst.has("candidate_flags"):
+                flags = inst.candidate_flags
+                sel = flags.nonzero().flatten().tolist()
+                if sel:
+                    dets = instances_to_coco_json(inst, inp["image_id"])
+                    for j in sel:
+                        d = dets[j]
+                        ig = int(flags[j] == 2)
+                        d.update(ignore_qe=ig, iscrowd=ig, area=d["bbox"][2] * d["bbox"][3], local_index=j)
+                        kept.append(d)
+            self._records.append((inp["image_id"], n, kept))
+
+    def evaluate(self):
+        recs = self._records
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+            dist.gather_object(recs, gathered, dst=0)
+            if dist.get_rank() != 0:
+                return {}
+            recs = list(itertools.chain(*gathered))
+        anns, offset = [], 0
+        for image_id, n, kept in recs:
+            for d in kept:
+                d["id"] = offset + d.pop("local_index") + 1
+                if self._map is not None:
+                    d["category_id"] = self._map[d["category_id"]]
+                anns.append(d)
+            offset += n
+        return {"num_images": len(recs), "num_detections": offset, "annotations": anns,
+                "num_candidates": sum(1 for a in anns if a["ignore_qe"] == 0)}
+
+
 def inference_shard(n, rank=None, world_size=None):
     """The reference's InferenceSampler rule (detectron2/data/samplers/distributed_sampler.py:191-194): rank r of W takes the
     contiguous block [r * ceil(n / W), min((r + 1) * ceil(n / W), n)) -- so that chain(*gather(...)) on rank 0 is in dataset order.
@@ -120,11 +172,11 @@ def inference_shard(n, rank=None, world_size=None):
 
 def inference_on_dataset(model, data_loader, evaluator):
     """Same contract as the reference's ``inference_on_dataset``: runs ``model`` over ``data_loader`` (an iterable with a
-    length, yielding list[dict] batches), feeds every (inputs, outputs) pair to ``evaluator.process`` and returns
+    length or a plain iterator, yielding list[dict] batches), feeds every (inputs, outputs) pair to ``evaluator.process`` and returns
     ``evaluator.evaluate()``; logs the reference's two timing lines."""
     logger = logging.getLogger(__name__)
     num_devices = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    total = len(data_loader)
+    total = len(data_loader) if hasattr(data_loader, "__len__") else "?"
     logger.info("Start inference on {} batches".format(total))
     evaluator.reset()
     start = time.time()

@@ -25,41 +25,62 @@ def assemble_tensors(shot_features: List[dict]) -> Tuple[torch.Tensor, torch.Ten
     return classes[sorter], desc[sorter]
 
 
-def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None):
+def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None, total: Optional[int] = None):
     """The ONE exchange step of the path (run_nearest_neighbours.py:303-309): every rank ends with the full bank,
-    rank-major order (== torch.cat(comm.all_gather(...)))."""
+    rank-major order (== torch.cat(comm.all_gather(...))).
+
+    ``total`` = the size of the whole support set, which every rank knows (it sharded the support DATASET by the
+    ``InferenceSampler`` rule, distributed_sampler.py:191-194): rank r then holds ``len(inference_shard(total, r, W))`` rows, the
+    shard is padded to ``ceil(total / W)`` rows, and the exchange is a SINGLE ``all_gather_into_tensor`` of one
+    ``[1 + ceil(total/W), D + 2]`` fp32 block per rank -- descriptors, bit-cast int64 classes, and a header row carrying the
+    shard's row count -- with no host synchronisation anywhere (sizes are not read back: the header only feeds a device-side
+    consistency flag, ``all_gather_bank.last_check``).  Without ``total`` (arbitrary uneven shards) a size exchange comes first."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return shot_classes, shot_descriptors
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = shot_descriptors.device
-    n = torch.tensor([shot_descriptors.shape[0]], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    mx, D = max(sizes), shot_descriptors.shape[1]
-    # one padded buffer carries descriptors and (bit-cast) classes: a single collective on the data path
-    pack = torch.zeros((mx, D + 2), dtype=torch.float32, device=dev)
-    pack[: sizes[dist.get_rank(group)], :D] = shot_descriptors.float()
-    pack[: sizes[dist.get_rank(group)], D:] = shot_classes.to(torch.int64).view(-1, 1).view(torch.float32).view(-1, 2) \
-        if shot_classes.numel() else pack[:0, D:]
-    out = torch.empty((world, mx, D + 2), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(out.view(world * mx, D + 2), pack, group=group) if dev.type == "cuda" else \
+    D = shot_descriptors.shape[1]
+    n_mine = shot_descriptors.shape[0]
+    if total is not None:
+        from .evaluation import inference_shard
+        sizes = [len(inference_shard(total, r, world)) for r in range(world)]
+        if sizes[rank] != n_mine:
+            raise ValueError(f"all_gather_bank: rank {rank} holds {n_mine} rows, the InferenceSampler rule gives {sizes[rank]} of {total}")
+        cap = max(sizes)
+    else:
+        n = torch.tensor([n_mine], dtype=torch.int64, device=dev)
+        gathered = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(gathered, n, group=group)
+        sizes = [int(s.item()) for s in gathered]
+        cap = max(sizes)
+    # one padded block carries the header, the descriptors and the (bit-cast) classes: a single collective on the data path
+    pack = torch.zeros((cap + 1, D + 2), dtype=torch.float32, device=dev)
+    pack[0, 0] = float(n_mine)
+    pack[1:1 + n_mine, :D] = shot_descriptors.float()
+    if n_mine:
+        pack[1:1 + n_mine, D:] = shot_classes.to(torch.int64).view(-1, 1).view(torch.float32).view(-1, 2)
+    out = torch.empty((world, cap + 1, D + 2), dtype=torch.float32, device=dev)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(out.view(world * (cap + 1), D + 2), pack, group=group)
+    else:
         dist.all_gather(list(out.unbind(0)), pack, group=group)
-    desc = torch.cat([out[r, : sizes[r], :D] for r in range(world)])
-    cls = torch.cat([out[r, : sizes[r], D:].contiguous().view(torch.int64).view(-1) for r in range(world)])
+    all_gather_bank.last_check = (out[:, 0, 0] == torch.tensor(sizes, dtype=torch.float32, device=dev)).all()   # device flag, not synced
+    desc = torch.cat([out[r, 1:1 + sizes[r], :D] for r in range(world)])
+    cls = torch.cat([out[r, 1:1 + sizes[r], D:].contiguous().view(torch.int64).view(-1) for r in range(world)])
     return cls, desc
+
+
+all_gather_bank.last_check = None
 
 
 def run_nearest_neighbours(shot_classes, shot_descriptors, query_features: List[dict], cosine: bool = True,
                            device: Optional[torch.device] = None, topk: int = 10):
     """tools/run_nearest_neighbours.py:142-162.  Sets ``top10_shots`` ([Qi, 10] int64 class votes, best first) on every
     image's ``Instances`` and returns the list, like the reference."""
-    if not cosine:
-        raise NotImplementedError("QUERY_EXPAND.COSINE_SIM=False (negative-cdist ranking) is not on the B200 path")
     if not query_features:
         return query_features
     device = device or (shot_descriptors.device if shot_descriptors.is_cuda else torch.device("cuda"))
-    bank = ops.KnnBank(shot_descriptors.to(device), shot_classes.to(device))
+    bank = ops.KnnBank(shot_descriptors.to(device), shot_classes.to(device), cosine=cosine)   # cosine=False: -cdist ranking (:154-159)
     counts = [len(d["instances"].get("crop_feats")) for d in query_features]
     feats = torch.cat([d["instances"].get("crop_feats") for d in query_features]).to(device)
     dt = [d["instances"].gt_classes if d["instances"].has("gt_classes") else torch.zeros(c, dtype=torch.int64)

@@ -139,6 +139,16 @@ class GeneralizedRCNN(_MiningModel):
         super().__init__(cfg, state_dict, device, use_cuda_graph, precision)
         self._host_ring = {}
         self._img_ring = OrderedDict()
+        self.candidate_filter = None    # a lvc_b200.candidates.CandidateFilter: results then carry `candidate_flags` (row a15 / f2)
+
+    def _pack(self, batched_inputs, images, outs, boxes, scores, classes, counts):
+        """One [n, 6k+1 (+k)] fp32 block per batch for the single D2H: boxes | scores | classes | (candidate flags) | count."""
+        cols = [boxes.view(len(images), -1), scores, classes.float()]
+        if self.candidate_filter is not None:
+            flags, _ = self.candidate_filter(boxes, scores, classes, counts, outs, [x.get("image_id") for x in batched_inputs])
+            cols.append(flags.float())
+        cols.append(counts.float()[:, None])
+        return torch.cat(cols, dim=1)
 
     @torch.no_grad()
     def inference_stream(self, batches):
@@ -189,7 +199,7 @@ class GeneralizedRCNN(_MiningModel):
             outs = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
             main.wait_event(ready)
             boxes, scores, classes, rows, counts = engine.run(images, outs)
-            packed = torch.cat([boxes.view(len(images), -1), scores, classes.float(), counts.float()[:, None]], dim=1)
+            packed = self._pack(batched_inputs, images, outs, boxes, scores, classes, counts)
             # two persistent pinned result buffers per shape, used alternately (a fresh pinned allocation per batch is a cudaHostAlloc:
             # milliseconds, and it serialises with the device on some hosts)
             key = (tuple(packed.shape), packed.dtype)
@@ -214,6 +224,8 @@ class GeneralizedRCNN(_MiningModel):
             inst.pred_boxes = Boxes(host[i, : 4 * k].view(k, 4)[:c].clone())
             inst.scores = host[i, 4 * k: 5 * k][:c].clone()
             inst.pred_classes = host[i, 5 * k: 6 * k][:c].to(torch.int64)
+            if host.shape[1] > 6 * k + 1:
+                inst.candidate_flags = host[i, 6 * k: 7 * k][:c].to(torch.int8)
             res.append({"instances": inst})
         return res
 
@@ -227,7 +239,7 @@ class GeneralizedRCNN(_MiningModel):
         outs = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)] if do_postprocess else sizes
         boxes, scores, classes, rows, counts = self.engine.run(images, outs)
         # one packed D2H per batch
-        host = torch.cat([boxes.view(len(images), -1), scores, classes.float(), counts.float()[:, None]], dim=1).cpu()
+        host = self._pack(batched_inputs, images, outs, boxes, scores, classes, counts).cpu()
         return self._unpack(host, _Done(), outs, scores.shape[1])
 
 

@@ -398,18 +398,21 @@ def apply_deltas_clip(boxes, deltas, weights, roi_image=None, image_sizes=None):
 class KnnBank:
     """Support bank after the all-gather: centred + normalised once (lvcb200_knn_prepare)."""
 
-    def __init__(self, bank, bank_cls):
+    def __init__(self, bank, bank_cls, cosine=True):
+        """cosine=False: QUERY_EXPAND.COSINE_SIM False, neighbours by -cdist (run_nearest_neighbours.py:154-159)."""
         _lib.require_cuda(bank, bank_cls)
         lib = _lib.load()
         self.bank = bank.detach().to(torch.float32).contiguous()
         self.cls = bank_cls.detach().to(torch.int64).contiguous()
         self.S, self.D = self.bank.shape
+        self.cosine = cosine
         self.prepared = torch.empty(lib.lvcb200_knn_prepared_bytes(self.S, self.D), dtype=torch.uint8, device=bank.device)
-        rc = lib.lvcb200_knn_prepare(_lib.ptr(self.bank), self.S, self.D, _lib.ptr(self.prepared), _lib.stream_ptr())
+        prep = lib.lvcb200_knn_prepare if cosine else lib.lvcb200_knn_prepare_euclid
+        rc = prep(_lib.ptr(self.bank), self.S, self.D, _lib.ptr(self.prepared), _lib.stream_ptr())
         _lib.check(rc, "lvcb200_knn_prepare")
 
     def tc_eligible(self):
-        return 64 <= self.S <= 4096 and self.D % 8 == 0 and 32 <= self.D <= 4096
+        return self.cosine and 64 <= self.S <= 4096 and self.D % 8 == 0 and 32 <= self.D <= 4096
 
     def verify(self, queries, query_cls, topk=10, knn=10, return_sim=False, path="auto"):
         """path: "auto" (tensor-core scores + exact re-rank when the bank shape allows it), "tc", or "simt" (exact fp32 FMA)."""
@@ -431,8 +434,9 @@ class KnnBank:
                                            ws.numel(), _lib.stream_ptr())
             _lib.check(rc, "lvcb200_knn_verify_tc")
         else:
-            rc = lib.lvcb200_knn_verify(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
-                                        topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep), _lib.stream_ptr())
+            fn = lib.lvcb200_knn_verify if self.cosine else lib.lvcb200_knn_verify_euclid
+            rc = fn(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
+                    topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep), _lib.stream_ptr())
             _lib.check(rc, "lvcb200_knn_verify")
         return dict(top_idx=top_idx, votes=votes, keep=keep, top_sim=sim)
 

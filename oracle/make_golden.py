@@ -173,6 +173,11 @@ def gold_knn():
     for k in (10, 5, 1):
         tool.get_nn_class_confirmatory(res, k)
         out[f"keep_k{k}"] = torch.cat([d["instances"].keep for d in res])
+    # QUERY_EXPAND.COSINE_SIM = False: the -cdist branch of the same function (:154-159)
+    res = tool.run_nearest_neighbours(torch.from_numpy(cls), torch.from_numpy(bank), qf, cosine=False)
+    out["votes_cdist"] = torch.cat([d["instances"].top10_shots for d in res])
+    tool.get_nn_class_confirmatory(res, 10)
+    out["keep_cdist_k10"] = torch.cat([d["instances"].keep for d in res])
     save("knn", **out)
 
 

@@ -154,36 +154,91 @@ def box_predictor(cfg, sd, x):
     return scores, deltas
 
 
-def detector_forward(cfg, sd, images, out_sizes=None, nms_mode=None, device="cuda", collect=None, emulate_bf16=False):
+def _roi_pooler_library(features, box_lists, output_size, sampling_ratio):
+    """ROIPooler.forward (detectron2/modeling/poolers.py:191-246) through torchvision.ops.roi_align -- the multi-threaded CPU
+    kernel the reference itself calls (roi_align.py:3,15).  Timing leg only; the scalar C restatement stays the checker."""
+    from torchvision.ops import roi_align
+    fmt = torch.cat([torch.cat([torch.full((len(b), 1), float(i)), torch.as_tensor(b, dtype=torch.float32).reshape(-1, 4)], 1)
+                     for i, b in enumerate(box_lists)])
+    lvls = torch.from_numpy(O.assign_boxes_to_levels(fmt[:, 1:].numpy(), 2, 5, 224, 4))
+    out = torch.zeros((len(fmt), features[0].shape[1], output_size, output_size))
+    for level, f in enumerate(features):
+        inds = torch.nonzero(lvls == level).flatten()
+        out[inds] = roi_align(torch.as_tensor(f), fmt[inds], output_size, 1.0 / (4 << level), sampling_ratio, True)
+    return out.numpy(), lvls.numpy()
+
+
+def _batched_nms_library(boxes, scores, idxs, thr, mode=None, device="cuda"):
+    """detectron2.layers.batched_nms (nms.py:10-29) through torchvision, as the reference calls it."""
+    from torchvision.ops import boxes as box_ops
+    b, s, i = torch.as_tensor(boxes, dtype=torch.float32).reshape(-1, 4), torch.as_tensor(scores, dtype=torch.float32), torch.as_tensor(idxs)
+    if len(b) < 40000:
+        return box_ops.batched_nms(b, s, i, thr).numpy()
+    keep = torch.zeros_like(s, dtype=torch.bool)
+    for c in torch.unique(i).tolist():
+        m = (i == c).nonzero().view(-1)
+        keep[m[box_ops.nms(b[m], s[m], thr)]] = True
+    k = keep.nonzero().view(-1)
+    return k[s[k].argsort(descending=True)].numpy()
+
+
+def detector_forward(cfg, sd, images, out_sizes=None, nms_mode=None, device="cuda", collect=None, emulate_bf16=False,
+                     library_ops=False, timings=None):
     """Full candidate-sourcing forward.  images: list of [3,H,W] tensors (BGR, 0..255).
 
     Returns per image dict(pred_boxes, scores, pred_classes).  ``collect`` (dict) receives intermediates.
     emulate_bf16=True restates the engine's precision policy (bf16 weights with folded FrozenBN, bf16 activation
     storage, fp32 accumulation) so that the engine can be checked layer by layer at bf16-rounding tolerance.
+    library_ops=True (CPU-baseline timing leg): RoIAlign and NMS run through torchvision's multi-threaded CPU kernels, which is
+    what the reference calls, instead of the scalar C restatement; ``timings`` (dict) accumulates seconds per stage.
     """
     global _EMULATE_BF16
     _EMULATE_BF16 = bool(emulate_bf16)
+    saved = O.batched_nms
+    if library_ops:
+        O.batched_nms = _batched_nms_library
     try:
-        return _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect)
+        return _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect, library_ops, timings)
     finally:
         _EMULATE_BF16 = False
+        O.batched_nms = saved
 
 
-def _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect):
+def _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect, library_ops=False, timings=None):
+    import time
+    t_last = [time.perf_counter()]
+
+    def lap(stage):
+        if timings is not None:
+            now = time.perf_counter()
+            timings[stage] = timings.get(stage, 0.0) + now - t_last[0]
+            t_last[0] = now
+
     with torch.no_grad():
         x, sizes = preprocess(cfg, images)
+        lap("preprocess")
         res_feats = resnet(cfg, sd, x, collect)
+        lap("resnet")
         if collect is not None:
             collect["features_res"] = res_feats
         feats = fpn(cfg, sd, res_feats)
+        lap("fpn")
         logits, deltas = rpn_head(sd, feats)
+        lap("rpn_head")
         names = ("p2", "p3", "p4", "p5", "p6")
         shapes = [tuple(feats[n].shape[-2:]) for n in names]
         props = rpn_proposals(cfg, logits, deltas, shapes, sizes, nms_mode, device)
-        pooled, lvls = O.roi_pooler([feats[n].numpy() for n in names[:4]], [p[0] for p in props],
-                                    cfg.pooler_resolution, sampling_ratio=cfg.pooler_sampling_ratio)
+        lap("rpn_proposals")
+        if library_ops:
+            pooled, lvls = _roi_pooler_library([feats[n] for n in names[:4]], [p[0] for p in props], cfg.pooler_resolution,
+                                               cfg.pooler_sampling_ratio)
+        else:
+            pooled, lvls = O.roi_pooler([feats[n].numpy() for n in names[:4]], [p[0] for p in props],
+                                        cfg.pooler_resolution, sampling_ratio=cfg.pooler_sampling_ratio)
+        lap("roi_pooler")
         xh = box_head(cfg, sd, pooled)
         scores, dl = box_predictor(cfg, sd, xh)
+        lap("box_head")
         probs = O.softmax_rows(scores.numpy())
         allp = np.concatenate([p[0] for p in props], 0)
         boxes = O.apply_deltas(dl.numpy(), allp, cfg.roi_bbox_weights)
@@ -201,6 +256,7 @@ def _detector_forward(cfg, sd, images, out_sizes, nms_mode, device, collect):
             oh, ow = out_sizes[i] if out_sizes else sizes[i]
             b2, keep = O.detector_postprocess(b, sizes[i], oh, ow)
             results.append(dict(pred_boxes=b2[keep], scores=s[keep], pred_classes=c[keep], rows=r[keep]))
+        lap("detections")
         return results
 
 

@@ -321,6 +321,27 @@ def knn_reference_form_torch(bank, bank_cls, queries, per_call=5, topk=10):
     return torch.cat(out).numpy()
 
 
+def knn_cdist_torch(bank, bank_cls, queries, query_cls=None, topk=10, knn=10, chunk=4096):
+    """The QUERY_EXPAND.COSINE_SIM = False branch (run_nearest_neighbours.py:154-159): sim = -torch.cdist(bank, query), no centring.
+    Returns dict(top_idx, top_sim, votes[, keep])."""
+    import torch
+    bank = torch.as_tensor(bank, dtype=torch.float32)
+    q = torch.as_tensor(queries, dtype=torch.float32)
+    bcls = torch.as_tensor(bank_cls)
+    sims, idxs = [], []
+    for s in range(0, q.shape[0], chunk):
+        sim = torch.cdist(bank.unsqueeze(0), q[s:s + chunk].unsqueeze(0)).squeeze(0).t().mul(-1.0)
+        v, i = sim.topk(topk, dim=-1)
+        sims.append(v)
+        idxs.append(i)
+    idx = torch.cat(idxs)
+    votes = bcls[idx]
+    out = dict(top_idx=idx.numpy(), top_sim=torch.cat(sims).numpy(), votes=votes.numpy())
+    if query_cls is not None:
+        out["keep"] = (torch.mode(votes[:, :knn], dim=1)[0] == torch.as_tensor(query_cls)).to(torch.uint8).numpy()
+    return out
+
+
 # ------------------------------------------------------------------------------------ candidate filter (a15)
 def select_candidates(image_id, category, score, area, image_area, train_imgs, novel_classes, k_min, k_max, ar=0.0, full=True,
                       top=False):

@@ -188,3 +188,86 @@ def test_lateral_conv_with_fused_topdown_add():
     _close(po.to_nchw(), want, True)
     full = out.view(n, H + 2, W + 2, Cout).float()
     assert float(full[:, 0].abs().max()) == 0 and float(full[:, -1].abs().max()) == 0 and float(full[:, :, 0].abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------------------- strict mode (SPLIT GEMM)
+def _pair(x):
+    full, S = ops.pair_split(x.float().contiguous())
+    return full, S
+
+
+def _merge(full, S, M):
+    return full[:M].float() + full[S:S + M].float()
+
+
+def _rel64(got, want):
+    return float((got.double() - want).norm() / (want.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 128, 256), (1000, 1024, 1024), (257, 64, 64), (5000, 16, 256), (200, 416, 1024)])
+@pytest.mark.parametrize("f32_out", [False, True])
+def test_split_gemm_matches_fp64(M, N, K, f32_out):
+    """Strict mode: fp32 operands carried as bf16 hi/lo pairs, three-term product on the bf16 tensor pipe.  Checker: the same
+    product in fp64 on the ORIGINAL fp32 operands; tolerance 3e-5 relative L2 (pair representation 2^-18 per operand, dropped
+    lo*lo term 2^-18, fp32 accumulation) -- two orders inside north_star's 1e-3, which a single bf16 product (4e-3) misses."""
+    if N < 64 and not f32_out:
+        pytest.skip("bf16 outputs use the staged epilogue (N >= 64)")
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    af, S = _pair(a)
+    out = ops.gemm(af, ops.split_weight(w).to(DEV), bias=bias, M=M, split_rows=S, out_dtype=torch.float32 if f32_out else torch.bfloat16)
+    got = out if f32_out else _merge(out, S, M)
+    want = a.double() @ w.double().t() + bias.double()
+    assert _rel64(got, want) < 3e-5
+    plain = ops.gemm(a.bfloat16(), w.bfloat16(), bias=bias, out_dtype=torch.float32)
+    assert _rel64(plain, want) > 20 * _rel64(got, want)      # the pair product really is that much tighter than one bf16 product
+
+
+def test_split_conv3x3_residual_relu_vs_fp32_conv():
+    g = torch.Generator(device="cpu").manual_seed(11)
+    n, C, H, W, O = 2, 64, 19, 27, 128
+    x = torch.randn(n, C, H, W, generator=g).to(DEV)
+    w = (torch.randn(O, C, 3, 3, generator=g) / (9 * C) ** 0.5).to(DEV)
+    b = torch.randn(O, generator=g).to(DEV)
+    r = torch.randn(n, O, H, W, generator=g).to(DEV)
+    xp, rp = ops.PairPlane.from_nchw(x), ops.PairPlane.from_nchw(r)
+    out = ops.PairPlane(torch.zeros((2 * xp.split_rows, O), dtype=torch.bfloat16, device=DEV), n, H, W, O)
+    PW = xp.PW
+    ops.gemm(xp.full, ops.split_weight(w.permute(0, 2, 3, 1).reshape(O, -1), 9).to(DEV), bias=b, residual=rp.full, out=out.full, relu=True,
+             taps=9, shifts=[(kh - 1) * PW + (kw - 1) for kh in range(3) for kw in range(3)], K=C, M=xp.M, plane_hw=(xp.PH, xp.PW),
+             split_rows=xp.split_rows)
+    want = torch.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1) + r.double())
+    assert _rel64(out.to_nchw(), want) < 3e-5
+    # the result is again a valid zero-bordered pair plane
+    assert float(out.t[:, 0].abs().max()) == 0 and float(out.lo[:, :, 0].abs().max()) == 0 and float(out.t[:, -1].abs().max()) == 0
+    # pair helpers round-trip: merge(split(x)) == x to 2^-17
+    m = xp.merged()
+    assert _rel64(m[:, 1:-1, 1:-1].permute(0, 3, 1, 2), x.double()) < 2 ** -17
+
+
+def test_pair_elementwise_kernels():
+    """maxpool / upsample-add / row_inv_norm / make_rois helper kernels of the strict path against torch."""
+    from lvc_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n, H, W, C = 2, 10, 14, 64
+    top = torch.randn(n, C, H, W, generator=g).to(DEV)
+    fine = torch.randn(n, C, 2 * H, 2 * W, generator=g).to(DEV)
+    tp, fp = ops.PairPlane.from_nchw(top), ops.PairPlane.from_nchw(fine)
+    _lib.check(lib.lvcb200_upsample2_add_pair(_lib.ptr(tp.full), tp.split_rows, n, H, W, C, _lib.ptr(fp.full), fp.split_rows, 2 * H, 2 * W,
+                                              _lib.stream_ptr()), "up")
+    want = fine.double() + F.interpolate(top, scale_factor=2, mode="nearest").double()
+    assert _rel64(fp.to_nchw(), want) < 1e-5
+    x = torch.randn(300, 1024, generator=g).to(DEV)
+    xf, S = _pair(x)
+    got = ops.row_inv_norm(xf, 20.0, 1e-5, lo_off=S * 1024, rows=300)
+    torch.testing.assert_close(got, 20.0 / (x.norm(dim=1) + 1e-5), rtol=1e-5, atol=0)
+    got = ops.row_inv_norm(x.bfloat16(), 20.0)
+    torch.testing.assert_close(got, 20.0 / (x.bfloat16().float().norm(dim=1) + 1e-5), rtol=1e-5, atol=0)
+    props = torch.randn(3, 50, 4, generator=g).to(DEV)
+    counts = torch.tensor([50, 0, 17], dtype=torch.int32, device=DEV)
+    rois, rimg = ops.make_rois(props, counts)
+    assert torch.equal(rois[:, 1:], props.view(-1, 4)) and torch.equal(rois[:, 0], torch.arange(3, device=DEV).repeat_interleave(50).float())
+    assert torch.equal(rimg.view(3, 50)[2], torch.where(torch.arange(50, device=DEV) < 17, 2, -1).int()) and int(rimg.view(3, 50)[1].max()) == -1

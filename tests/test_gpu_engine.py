@@ -121,6 +121,139 @@ def test_engine_stagewise_vs_oracle(depth, layer, sizes):
         np.testing.assert_allclose(np.sort(boxes[i, :k].cpu().numpy(), 0), np.sort(wb[keep], 0), rtol=1e-3, atol=1e-2)
 
 
+def _run_debug(cfg, sd, ims, precision, outs=None):
+    eng = DetectorEngine(cfg, sd, precision=precision)
+    eng.debug = {}
+    res = eng.run([im.cuda() for im in ims], outs)
+    torch.cuda.synchronize()
+    return eng, res
+
+
+@pytest.mark.parametrize("depth,layer,sizes", [(50, "FastRCNNOutputLayers", [(320, 416), (300, 400)]),
+                                               (101, "CosineSimOutputLayers", [(256, 320)])])
+def test_strict_engine_vs_fp32_oracle(depth, layer, sizes):
+    """STRICT mode against the plain fp32 oracle (no bf16 emulation): BASELINE.json's contract -- features / logits / scores within
+    1e-3 relative, index work identical wherever the fp32 inputs are not within rounding noise of a tie."""
+    cfg = DetectorConfig(depth=depth, output_layer=layer)
+    sd = synthetic_state_dict(cfg, 0, randomize_bn=True)
+    ims = _images(100, sizes)
+    n = len(ims)
+    eng, (boxes, scores, classes, rows, counts) = _run_debug(cfg, sd, ims, "strict")
+    dbg = eng.debug
+    col = {}
+    ref = OM.detector_forward(cfg, sd, ims, device="cuda", collect=col)
+    rels = {"stem": _rel(dbg["stem_pool"].to_nchw().cpu(), col["stem"])}
+    for l in (2, 3, 4, 5):
+        rels[f"res{l}"] = _rel(dbg["feats"][l].to_nchw().cpu(), col["features_res"][f"res{l}"])
+    for l in (2, 3, 4, 5, 6):
+        rels[f"p{l}"] = _rel(dbg["pyramid"][l].to_nchw().cpu(), col["features"][f"p{l}"])
+    e_logits, e_deltas = _rpn_head_arrays(eng, n)
+    for i in range(5):
+        rels[f"rpn_logits{i}"] = _rel(torch.from_numpy(e_logits[i]), col["rpn_logits"][i])
+        rels[f"rpn_deltas{i}"] = _rel(torch.from_numpy(e_deltas[i]), col["rpn_deltas"][i])
+    print("strict rel-L2 vs fp32 oracle:", {k: f"{v:.2e}" for k, v in rels.items()})
+    assert max(rels.values()) < 1e-3, rels
+    # proposals: the same boxes in the same order except where fp32 logits tie within rounding noise
+    same = 0
+    for i in range(n):
+        c = int(dbg["prop_counts"][i])
+        want = col["proposals"][i][0]
+        assert abs(c - len(want)) <= 2
+        m = min(c, len(want))
+        same += int((np.abs(dbg["props"][i, :m].cpu().numpy() - want[:m]).max(1) < 1e-2).sum())
+    tot = sum(len(p[0]) for p in col["proposals"])
+    print(f"strict proposals identical in place: {same}/{tot}")
+    assert same >= 0.97 * tot
+    # detections
+    ok = tot_d = 0
+    for i in range(n):
+        k = int(counts[i])
+        gb, gs, gc = ref[i]["pred_boxes"], ref[i]["scores"], ref[i]["pred_classes"]
+        tot_d += len(gs)
+        if k == 0 or len(gs) == 0:
+            continue
+        iou = _iou(gb, boxes[i, :k].cpu().numpy())
+        j = iou.argmax(1)
+        good = (iou.max(1) > 0.95) & (classes[i, :k].cpu().numpy()[j] == gc) & (np.abs(scores[i, :k].cpu().numpy()[j] - gs) < 1e-3 * np.maximum(gs, 1e-3) + 1e-5)
+        ok += int(good.sum())
+    print(f"strict detections reproduced within 1e-3: {ok}/{tot_d}")
+    assert ok >= 0.97 * tot_d
+
+
+@pytest.mark.parametrize("precision", ["strict", "bf16"])
+@pytest.mark.parametrize("name", ["e2e_r101_cosine", "e2e_r101_b8"])
+def test_engine_vs_reference_golden_e2e(golden, name, precision):
+    """Both engine modes against the UNMODIFIED reference's fp32 outputs (oracle/make_golden.py): the candidate-sourcing config on one
+    small image, and BASELINE config #2 itself (R101-FPN, batch 8 x 3x800x1333, the bench's images).  The strict mode must meet
+    north_star's 1e-3; the bf16 throughput mode is measured and held to the tolerance DESIGN.md states for it."""
+    from lvc_b200.testing import e2e_parity_metrics
+    g = golden(name)
+    cfg = DetectorConfig(depth=int(g["depth"]), output_layer=str(g["output_layer"]), score_thresh_test=float(g["score_thresh"]))
+    sizes = [tuple(int(v) for v in s) for s in g["sizes"]]
+    outs = [tuple(int(v) for v in s) for s in g["out_sizes"]]
+    ims = _images(int(g["seed"]), sizes)
+    eng, (boxes, scores, classes, rows, counts) = _run_debug(cfg, synthetic_state_dict(cfg, 0), ims, precision, outs)
+    m = e2e_parity_metrics(g, eng.debug, boxes, scores, classes, counts)
+    print(f"{name} [{precision}]:", m)
+    worst = max(m["features_rel_l2"].values())
+    if precision == "strict":
+        assert worst < 1e-3 and m["proposals_reproduced"] > 0.98 and m["detections_reproduced"] > 0.97
+        assert m["max_score_delta_matched"] < 1e-3
+    else:
+        assert worst < 2e-2 and m["proposals_reproduced"] > 0.5 and m["detections_reproduced"] > 0.6
+
+
+def test_strict_cuda_graph_and_api():
+    """precision='strict' through the public model API and a CUDA-graph replay: identical to the eager strict run."""
+    cfg = DetectorConfig(depth=50)
+    sd = synthetic_state_dict(cfg, 0)
+    ims = [im.cuda() for im in _images(7, [(192, 256), (192, 256)])]
+    eager = DetectorEngine(cfg, sd, precision="strict").run(ims)
+    eng = DetectorEngine(cfg, sd, use_cuda_graph=True, precision="strict")
+    for _ in range(3):
+        out = eng.run(ims)
+    torch.cuda.synchronize()
+    for a, b in zip(eager, out):
+        assert torch.equal(a, b)
+    model = GeneralizedRCNN(cfg, sd, precision="strict", use_cuda_graph=False)
+    res = model([{"image": im.cpu()} for im in ims])
+    assert len(res) == 2 and len(res[0]["instances"]) == int(eager[4][0])
+
+
+def test_shape_lru_and_back_to_back_runs():
+    """(a) shape-keyed state is LRU-bounded -- cycling through more input shapes than max_shapes keeps working and
+    reproduces the first shape's results after it was evicted; (b) back-to-back run() calls with different images and no host
+    sync in between keep their own metadata (pinned staging ring)."""
+    cfg = DetectorConfig(depth=50)
+    sd = synthetic_state_dict(cfg, 0)
+    eng = DetectorEngine(cfg, sd, use_cuda_graph=True, max_shapes=2)
+    shapes = [(128, 160), (160, 192), (192, 224)]
+    ims = {s: [im.cuda() for im in _images(40 + i, [s])] for i, s in enumerate(shapes)}
+    first = [t.clone() for t in eng.run(ims[shapes[0]])]
+    for _ in range(2):
+        for s in shapes:
+            for _ in range(3):
+                eng.run(ims[s])
+    assert len(eng._states) == 2
+    again = eng.run(ims[shapes[0]])
+    torch.cuda.synchronize()
+    for a, b in zip(first, again):
+        assert torch.equal(a, b)
+    eng2 = DetectorEngine(cfg, sd)
+    a_im, b_im = _images(60, [(128, 160)])[0].cuda(), _images(61, [(100, 150)])[0].cuda()
+    want_a = [t.clone() for t in eng2.run([a_im])]
+    want_b = [t.clone() for t in eng2.run([b_im])]
+    torch.cuda.synchronize()
+    got = []
+    for _ in range(6):                      # no synchronisation between calls
+        got.append([t.clone() for t in eng2.run([a_im])])
+        got.append([t.clone() for t in eng2.run([b_im])])
+    torch.cuda.synchronize()
+    for k, r in enumerate(got):
+        for x, y in zip(r, want_a if k % 2 == 0 else want_b):
+            assert torch.equal(x, y)
+
+
 def test_model_api_vs_golden_fp32(golden):
     """Public API (list[dict] in, list[dict{'instances'}] out) against the reference's fp32 outputs on config #1's family."""
     g = golden("e2e_r50_base")

@@ -273,6 +273,30 @@ def test_knn_golden(golden):
         assert np.array_equal(r["keep"].cpu().numpy(), g[f"keep_k{k}"].astype(np.uint8))
 
 
+def test_knn_cdist_branch(golden):
+    """QUERY_EXPAND.COSINE_SIM = False: neighbours by -cdist (run_nearest_neighbours.py:154-159) against the reference's votes and,
+    tie-aware, against torch.cdist on a larger problem."""
+    g = golden("knn")
+    bank = ops.KnnBank(cu(g["bank"]), cu(g["bank_cls"]), cosine=False)
+    r = bank.verify(cu(g["queries"]), cu(g["query_cls"]), topk=10, knn=10)
+    assert np.array_equal(np.sort(r["votes"].cpu().numpy(), 1), np.sort(g["votes_cdist"], 1))
+    assert np.array_equal(r["keep"].cpu().numpy(), g["keep_cdist_k10"].astype(np.uint8))
+    rng = np.random.default_rng(22)
+    S, D, Q = 300, 384, 2000
+    cls = np.repeat(np.arange(20), S // 20).astype(np.int64)
+    b = rng.standard_normal((S, D)).astype(np.float32) + 1.0
+    q = rng.standard_normal((Q, D)).astype(np.float32) + 1.0
+    qc = rng.integers(0, 20, Q).astype(np.int64)
+    want = O.knn_cdist_torch(b, cls, q, qc)
+    got = ops.KnnBank(cu(b), cu(cls), cosine=False).verify(cu(q), cu(qc), return_sim=True)
+    gi, gs = got["top_idx"].cpu().numpy(), got["top_sim"].cpu().numpy()
+    np.testing.assert_allclose(gs, want["top_sim"], rtol=1e-4, atol=1e-4)
+    bad = gi != want["top_idx"]
+    assert bad.mean() < 2e-3 and np.all(np.abs(gs[bad] - want["top_sim"][bad]) < 1e-3)
+    rows_bad = bad.any(1)
+    assert np.array_equal(got["keep"].cpu().numpy()[~rows_bad], want["keep"][~rows_bad])
+
+
 def test_knn_vs_oracle_tie_aware():
     """Index parity against the scalar oracle; positions may differ only where the oracle's similarities tie to 1e-5."""
     rng = np.random.default_rng(21)
@@ -388,3 +412,73 @@ def test_fast_rcnn_losses(golden):
     want = O.fast_rcnn_losses(g["frcnn_logits"], g["frcnn_deltas"][:, :4], g["frcnn_gt_classes"], g["frcnn_props"], g["frcnn_gt_boxes"]) / 1024
     ls = fast_rcnn_losses(t("frcnn_logits"), dl4, t("frcnn_gt_classes"), t("frcnn_props"), t("frcnn_gt_boxes"))
     assert abs(float(ls["loss_box_reg"]) - want[1]) <= 1e-5 * want[1]
+
+
+# ---------------------------------------------------------------------------------------------- a15 / f2: device-side candidate filter
+@pytest.mark.parametrize("tag,kw", [("score_full", dict(full=True, k_min=0.8, k_max=1.0, ar=0.0)),
+                                    ("score_nofull", dict(full=False, k_min=0.5, k_max=0.9, ar=0.05))])
+def test_candidate_filter_device_vs_reference(golden, tag, kw):
+    """lvcb200_candidate_filter on per-image detection blocks against the reference's get_ret_anns output
+    (tests/golden/candidates.npz, tools/create_coco_dataset_from_dets_all.py:129-193) and the host mirror: flags bit-exact."""
+    from lvc_b200.candidates import CandidateFilter, select_candidates
+    g = golden("candidates")
+    ids, cat, sc, area, iarea = g["image_id"], g["category"], g["score"], g["area"], g["image_area"]
+    novel = [int(c) for c in g["novel"]]
+    train = {c: set(int(v) for v in g[f"train_{c}"]) for c in novel}
+    w = np.sqrt(area).astype(np.float32)
+    h = np.where(w > 0, area / np.maximum(w, 1e-30), 1.0).astype(np.float32)
+    uniq = np.unique(ids)
+    topk = max(int((ids == u).sum()) for u in uniq)
+    n = len(uniq)
+    boxes = np.zeros((n, topk, 4), np.float32); scores = np.zeros((n, topk), np.float32); classes = np.zeros((n, topk), np.int64)
+    counts = np.zeros(n, np.int32); where = np.full((n, topk), -1, np.int64); sizes = []
+    for i, u in enumerate(uniq):
+        sel = np.nonzero(ids == u)[0]
+        counts[i] = len(sel)
+        boxes[i, :len(sel), 2], boxes[i, :len(sel), 3] = w[sel], h[sel]
+        scores[i, :len(sel)], classes[i, :len(sel)], where[i, :len(sel)] = sc[sel], cat[sel], sel
+        sizes.append((1.0, float(iarea[sel[0]])))                       # height * width = the image record's area
+    filt = CandidateFilter(novel, kw["k_min"], kw["k_max"], kw["ar"], kw["full"], train, num_classes=15)
+    flags, n_keep = filt(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(classes).cuda(),
+                         torch.from_numpy(counts).cuda(), sizes, [int(u) for u in uniq])
+    flags = flags.cpu().numpy()
+    got = np.zeros(len(ids), np.int8)
+    got[where[where >= 0]] = flags[where >= 0]
+    assert np.array_equal(got, g["flags_" + tag])
+    assert int((flags[where < 0] != 0).sum()) == 0                      # padding slots are dropped
+    assert np.array_equal(n_keep.cpu().numpy(), (flags == 1).sum(1))
+    a2 = torch.from_numpy(w.astype(np.float64) * h.astype(np.float64))
+    mirror = select_candidates(torch.from_numpy(ids), torch.from_numpy(cat), torch.from_numpy(sc), a2, torch.from_numpy(iarea), train, novel,
+                               kw["k_min"], kw["k_max"], kw["ar"], kw["full"])
+    assert np.array_equal(got, mirror.numpy())
+
+
+def test_model_candidate_flags_through_public_api():
+    """model.candidate_filter: flags travel in the batch's one packed D2H and match the host mirror on the returned detections."""
+    from lvc_b200.candidates import CandidateFilter, select_candidates
+    from lvc_b200.config import DetectorConfig
+    from lvc_b200.evaluation import CandidateCollector, inference_on_dataset
+    from lvc_b200.modeling import GeneralizedRCNN
+    from lvc_b200.weights import synthetic_state_dict
+    cfg = DetectorConfig(depth=50, score_thresh_test=0.0)
+    model = GeneralizedRCNN(cfg, synthetic_state_dict(cfg, 0), use_cuda_graph=True)
+    novel = list(range(0, 80, 4))
+    ims = [torch.rand(3, 160, 200, generator=torch.Generator().manual_seed(70 + i)) * 255 for i in range(6)]
+    loader = [[{"image": ims[2 * b + j], "image_id": 500 + 2 * b + j, "height": 320, "width": 400} for j in range(2)] for b in range(3)]
+    plain = [model(b) for b in loader]
+    s_all = torch.cat([r["instances"].scores for b in plain for r in b])
+    k_min = float(s_all.median())                                        # a threshold that splits the detections
+    model.candidate_filter = CandidateFilter(novel, k_min, 1.0, ar=0.0, full=True, train_imgs={0: {501}})
+    res = inference_on_dataset(model, iter(loader), CandidateCollector())   # an ITERATOR: the driver must not need len() / a list
+    flat = [r["instances"] for b in (model(b) for b in loader) for r in b]
+    img = torch.cat([torch.full((len(i),), 500 + k) for k, i in enumerate(flat)])
+    boxes = torch.cat([i.pred_boxes.tensor for i in flat])
+    area = ((boxes[:, 2] - boxes[:, 0]).double() * (boxes[:, 3] - boxes[:, 1]).double())
+    want = select_candidates(img, torch.cat([i.pred_classes for i in flat]), torch.cat([i.scores for i in flat]), area,
+                             torch.full((len(img),), 320.0 * 400.0, dtype=torch.float64), {0: {501}}, novel, k_min, 1.0, 0.0, True)
+    got = torch.cat([i.candidate_flags for i in flat])
+    assert torch.equal(got, want) and int((got == 1).sum()) > 0
+    assert res["num_images"] == 6 and res["num_detections"] == len(img)
+    assert res["num_candidates"] == int((want == 1).sum()) and len(res["annotations"]) == int((want != 0).sum())
+    ids = [a["id"] for a in res["annotations"]]
+    assert ids == sorted(ids) and ids == (want != 0).nonzero().flatten().add(1).tolist()   # loadRes' running index over all detections

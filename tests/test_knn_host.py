@@ -48,6 +48,22 @@ def _worker(rank, world, port, ret):
     cls = torch.arange(n, dtype=torch.int64) + (1 << 40) * rank   # exercises the 64-bit class packing
     c, d = all_gather_bank(cls, desc)
     ret[rank] = (c.clone(), d.clone())
+    # single-collective form: the support set of 7 rows sharded by the InferenceSampler rule (4 + 3), sizes known to every rank
+    from lvc_b200.evaluation import inference_shard
+    all_d = torch.arange(7 * 8, dtype=torch.float32).view(7, 8)
+    all_c = torch.arange(7, dtype=torch.int64) * (1 << 33)
+    mine = inference_shard(7, rank, world)
+    calls = []
+    orig = dist.all_gather
+    dist.all_gather = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    c2, d2 = all_gather_bank(all_c[mine.start:mine.stop], all_d[mine.start:mine.stop], total=7)
+    dist.all_gather = orig
+    ret[f"single{rank}"] = (c2.clone(), d2.clone(), len(calls), bool(all_gather_bank.last_check))
+    try:
+        all_gather_bank(all_c[:1], all_d[:1], total=7)
+        ret[f"err{rank}"] = False
+    except ValueError:
+        ret[f"err{rank}"] = True
     dist.destroy_process_group()
 
 
@@ -61,3 +77,7 @@ def test_all_gather_bank_gloo_world2():
     for r in (0, 1):
         c, d = ret[r]
         assert torch.equal(d, want_d) and torch.equal(c, want_c)
+        c2, d2, ncalls, ok = ret[f"single{r}"]
+        assert torch.equal(d2, torch.arange(56, dtype=torch.float32).view(7, 8)) and torch.equal(c2, torch.arange(7) * (1 << 33))
+        assert ncalls == 1 and ok            # exactly one collective on the data path (gloo: the list form of all_gather)
+        assert ret[f"err{r}"]                # a shard that contradicts the sampler rule is refused before any communication
