@@ -3,8 +3,12 @@
 //       (:116-125), class-specific apply_deltas + clip for the surviving (roi, class) pairs only (:440-458, :110-113;
 //       the reference decodes all R x K boxes), appended to per-(image, class) candidate lists.
 //   det_class_nms_kernel    : CTA per (image, class) -- in-CTA sort by score, greedy NMS (== batched_nms over class ids, :128)
-//   det_merge_kernel        : CTA per image -- rank kept candidates over all classes by score, first topk (:129-131),
-//       then detector_postprocess: rescale, clip, drop empty (postprocessing.py:10-79).
+//   det_rank_kernel         : CTA per (image, class) -- global rank of the class's first topk kept candidates among the first topk
+//       of every other class list (all lists are score-sorted, so nothing beyond a list's first topk entries can reach the image's
+//       top-k, :129-131): the K x topk score table sits in shared memory, ranks come from binary searches in it.
+//   det_finalize_kernel     : warp per image -- detector_postprocess: rescale, clip, drop empty (postprocessing.py:10-79), ordered.
+//   det_merge_kernel        : the one-CTA-per-image form of the two (global-memory searches); kept for K * topk tables that do
+//       not fit in shared memory ("all detections" calls).
 #include "nms_core.cuh"
 #include "sort_core.cuh"
 
@@ -241,6 +245,91 @@ det_merge_kernel(int K, int topk, const int* __restrict__ kcount, const float* _
   }
 }
 
+// Parallel form of the merge.  With a realistic score distribution (or SCORE_THRESH_TEST 0.0) tens of thousands of candidates
+// per image survive the per-class NMS; the single-CTA merge above then spends milliseconds in dependent global-memory binary
+// searches (0.95 ms for 8 images of random logits, ~15 ms at threshold 0 -- profiles/r02_ops_ncu.md).  Only the first topk entries
+// of each sorted class list can reach the image's top-k, so K * topk scores (32 KB for 80 x 100) are all that has to be searched.
+__global__ void __launch_bounds__(128)
+det_rank_kernel(int K, int topk, const int* __restrict__ kcount, const float* __restrict__ cscore, const int* __restrict__ crow,
+                const float4* __restrict__ cbox, float4* __restrict__ tmp_boxes, float* __restrict__ tmp_scores, int* __restrict__ tmp_cls,
+                int* __restrict__ tmp_rows) {
+  extern __shared__ int dr_smem[];
+  int* s_cnt = dr_smem;                                        // K counts, clamped to topk
+  float* s_score = reinterpret_cast<float*>(dr_smem + K);      // [K][topk]
+  const int img = blockIdx.y, c = blockIdx.x;
+  const int n = min(kcount[img * K + c], topk);
+  if (n == 0) return;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s_cnt[i] = min(kcount[img * K + i], topk);
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * topk; i += blockDim.x) {
+    const int c2 = i / topk, p = i - c2 * topk;
+    s_score[i] = p < s_cnt[c2] ? cscore[(size_t)(img * K + c2) * kMaxRois + p] : -INFINITY;
+  }
+  __syncthreads();
+  const size_t base = (size_t)(img * K + c) * kMaxRois;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) {
+    const float s = s_score[c * topk + p];
+    const int row = crow[base + p];
+    int rank = p;
+    for (int c2 = 0; c2 < K && rank < topk; c2++) {
+      const int n2 = s_cnt[c2];
+      if (c2 == c || n2 == 0) continue;
+      const float* a = s_score + c2 * topk;
+      int g = count_greater_desc(a, n2, s);
+      if (g < n2 && a[g] == s) {   // ties: the reference's stable sort keeps nonzero() order = (row, class) ascending
+        const int* r2 = crow + (size_t)(img * K + c2) * kMaxRois;
+        while (g < n2 && a[g] == s && (r2[g] < row || (r2[g] == row && c2 < c))) g++;
+      }
+      rank += g;
+    }
+    if (rank < topk) {
+      tmp_boxes[(size_t)img * topk + rank] = cbox[base + p];
+      tmp_scores[(size_t)img * topk + rank] = s;
+      tmp_cls[(size_t)img * topk + rank] = c;
+      tmp_rows[(size_t)img * topk + rank] = row;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+det_finalize_kernel(int K, int topk, const int* __restrict__ kcount, const int32_t* __restrict__ image_sizes,
+                    const int32_t* __restrict__ out_sizes, const float4* __restrict__ tmp_boxes, const float* __restrict__ tmp_scores,
+                    const int* __restrict__ tmp_cls, const int* __restrict__ tmp_rows, float4* __restrict__ det_boxes,
+                    float* __restrict__ det_scores, int64_t* __restrict__ det_classes, int64_t* __restrict__ det_rows,
+                    int32_t* __restrict__ det_counts) {
+  const int img = blockIdx.x, lane = threadIdx.x;
+  int total = 0;
+  for (int c = lane; c < K; c += 32) total += kcount[img * K + c];
+  for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  const int n_out = total < topk ? total : topk;
+  const float ih = (float)image_sizes[img * 2], iw = (float)image_sizes[img * 2 + 1];
+  const int oh = out_sizes[img * 2], ow = out_sizes[img * 2 + 1];
+  const float sx = __fdiv_rn((float)ow, iw), sy = __fdiv_rn((float)oh, ih);
+  int outp = 0;
+  for (int i0 = 0; i0 < n_out; i0 += 32) {
+    int i = i0 + lane;
+    bool ok = false; float4 b = make_float4(0, 0, 0, 0);
+    if (i < n_out) {
+      b = tmp_boxes[(size_t)img * topk + i];
+      b.x = fminf(fmaxf(__fmul_rn(b.x, sx), 0.f), (float)ow); b.y = fminf(fmaxf(__fmul_rn(b.y, sy), 0.f), (float)oh);
+      b.z = fminf(fmaxf(__fmul_rn(b.z, sx), 0.f), (float)ow); b.w = fminf(fmaxf(__fmul_rn(b.w, sy), 0.f), (float)oh);
+      ok = (__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f);
+    }
+    unsigned int m = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      size_t o = (size_t)img * topk + outp + __popc(m & ((1u << lane) - 1u));
+      det_boxes[o] = b; det_scores[o] = tmp_scores[(size_t)img * topk + i];
+      det_classes[o] = tmp_cls[(size_t)img * topk + i]; det_rows[o] = tmp_rows[(size_t)img * topk + i];
+    }
+    outp += __popc(m);
+  }
+  for (int i = outp + lane; i < topk; i += 32) {
+    size_t o = (size_t)img * topk + i;
+    det_boxes[o] = make_float4(0, 0, 0, 0); det_scores[o] = 0.f; det_classes[o] = -1; det_rows[o] = -1;
+  }
+  if (lane == 0) det_counts[img] = outp;
+}
+
 // Box2BoxTransform.apply_deltas (box_regression.py:73-110) for class-agnostic deltas + Boxes.clip: the per-stage box update of
 // the box corrector (BoxOnlyLayersCascade.predict_boxes roi_heads_cascade.py:197-211; _create_proposals_from_boxes
 // cascade_rcnn.py:348-369).
@@ -322,6 +411,24 @@ extern "C" int lvcb200_detections(const float* cls_logits, int64_t logit_pitch, 
   det_class_nms_kernel<<<p->n_images * K, 256, 0, s>>>(K, p->nms_thresh, p->nms_mode, hdr, ccount, (float*)(ws + w.off_cscore),
                                                        (int*)(ws + w.off_crow), (float4*)(ws + w.off_cbox), (int*)(ws + w.off_kcount));
   if ((rc = check_launch("det_class_nms_kernel"))) return rc;
+  const size_t rank_smem = sizeof(int) * K + sizeof(float) * (size_t)K * topk;
+  if (rank_smem <= 160 * 1024) {   // the usual case (80 x 100: 32 KB): parallel rank + finalize
+    static size_t smem_set = 0;
+    if (rank_smem > smem_set && rank_smem > 48 * 1024) {
+      LVC_CUDA(cudaFuncSetAttribute(det_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+      smem_set = rank_smem;
+    }
+    det_rank_kernel<<<dim3(K, p->n_images), 128, rank_smem, s>>>(
+        K, topk, (const int*)(ws + w.off_kcount), (const float*)(ws + w.off_cscore), (const int*)(ws + w.off_crow),
+        (const float4*)(ws + w.off_cbox), (float4*)(ws + w.off_tmp_boxes), (float*)(ws + w.off_tmp_scores), (int*)(ws + w.off_tmp_cls),
+        (int*)(ws + w.off_tmp_rows));
+    if ((rc = check_launch("det_rank_kernel"))) return rc;
+    det_finalize_kernel<<<p->n_images, 32, 0, s>>>(
+        K, topk, (const int*)(ws + w.off_kcount), image_sizes, out_sizes, (const float4*)(ws + w.off_tmp_boxes),
+        (const float*)(ws + w.off_tmp_scores), (const int*)(ws + w.off_tmp_cls), (const int*)(ws + w.off_tmp_rows), (float4*)det_boxes,
+        det_scores, det_classes, det_rows, det_counts);
+    return check_launch("det_finalize_kernel");
+  }
   det_merge_kernel<<<p->n_images, 256, sizeof(int) * K, s>>>(
       K, topk, (const int*)(ws + w.off_kcount), (const float*)(ws + w.off_cscore), (const int*)(ws + w.off_crow),
       (const float4*)(ws + w.off_cbox), image_sizes, out_sizes, (float4*)(ws + w.off_tmp_boxes), (float*)(ws + w.off_tmp_scores),

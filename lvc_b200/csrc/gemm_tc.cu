@@ -296,7 +296,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         zero_row = (y == 0) || (y == (unsigned)p.plane_h - 1) || (x == 0) || (x == (unsigned)p.plane_w - 1);
         if constexpr (UPS) {   // row of the coarser plane under this pixel: interior (y, x) -> ((y - 1) / 2 + 1, (x - 1) / 2 + 1)
           const long long img = m / plane;
-          up_row = zero_row ? nullptr
+          // rows past M (the tail of the last tile) belong to no image: they must not index the coarse plane (they would read past its end)
+          up_row = (zero_row || m >= p.M) ? nullptr
                             : p.up + ((img * p.up_ph + (long long)(((y - 1) >> 1) + 1)) * p.up_pw + (((x - 1) >> 1) + 1)) * p.ldu + n0;
         }
       }

@@ -32,7 +32,8 @@ def box_iou_np(a, b):
 def e2e_parity_metrics(g, debug, boxes, scores, classes, counts):
     """Engine outputs against a reference-generated end-to-end fixture (tests/golden/e2e_*.npz, written by oracle/make_golden.py
     from the UNMODIFIED fp32 reference): per-level feature relative L2 on the fixture's sampled elements, the fraction of the
-    reference's proposals / detections the engine reproduces, and the largest score difference among matched detections.
+    reference's proposals the engine reproduces (a box within 0.05 px; and, looser, a box of IoU > 0.9), the fraction of its
+    detections it reproduces (same class, IoU > 0.9), and the largest score / box difference among matched detections.
     ``debug`` is DetectorEngine.debug after a run; boxes / scores / classes / counts the run's outputs."""
     import torch
     out = {"features_rel_l2": {}}
@@ -42,7 +43,7 @@ def e2e_parity_metrics(g, debug, boxes, scores, classes, counts):
         got = debug["pyramid"][l].to_nchw().flatten()[idx.to(debug["pyramid"][l].t.device)].double().cpu().numpy()
         out["features_rel_l2"][f"p{l}"] = float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-30))
     n = len(g["sizes"])
-    pm = pn = dm = dn = 0
+    pm = pn = dm = dn = pi90 = 0
     max_ds, max_db = 0.0, 0.0
     for i in range(n):
         rp = g[f"prop_boxes{i}"]
@@ -51,6 +52,7 @@ def e2e_parity_metrics(g, debug, boxes, scores, classes, counts):
         if len(rp) and len(ours):
             d = np.abs(rp[:, None, :] - ours[None, :, :]).max(-1)             # [ref, ours] max coordinate difference (px)
             pm += int((d.min(1) < 0.05).sum())
+            pi90 += int((box_iou_np(rp, ours).max(1) > 0.9).sum())
         pn += len(rp)
         gb, gs, gc = g[f"det_boxes{i}"], g[f"det_scores{i}"], g[f"det_classes{i}"]
         k = int(counts[i])
@@ -65,6 +67,6 @@ def e2e_parity_metrics(g, debug, boxes, scores, classes, counts):
             if ok.any():
                 max_ds = max(max_ds, float(np.abs(os_[j][ok] - gs[ok]).max()))
                 max_db = max(max_db, float(np.abs(ob[j][ok] - gb[ok]).max()))
-    out.update(proposals_reproduced=pm / max(pn, 1), detections_reproduced=dm / max(dn, 1), n_ref_detections=dn,
+    out.update(proposals_reproduced=pm / max(pn, 1), proposals_matched_iou90=pi90 / max(pn, 1), detections_reproduced=dm / max(dn, 1), n_ref_detections=dn,
                n_detections=int(sum(int(counts[i]) for i in range(n))), max_score_delta_matched=max_ds, max_box_delta_px_matched=max_db)
     return out

@@ -462,7 +462,7 @@ def test_model_candidate_flags_through_public_api():
     from lvc_b200.weights import synthetic_state_dict
     cfg = DetectorConfig(depth=50, score_thresh_test=0.0)
     model = GeneralizedRCNN(cfg, synthetic_state_dict(cfg, 0), use_cuda_graph=True)
-    novel = list(range(0, 80, 4))
+    novel = list(range(80))
     ims = [torch.rand(3, 160, 200, generator=torch.Generator().manual_seed(70 + i)) * 255 for i in range(6)]
     loader = [[{"image": ims[2 * b + j], "image_id": 500 + 2 * b + j, "height": 320, "width": 400} for j in range(2)] for b in range(3)]
     plain = [model(b) for b in loader]
