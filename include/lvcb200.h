@@ -193,10 +193,14 @@ int lvcb200_knn_prepare_euclid(const float* bank, int S, int D, void* bank_prepa
 int lvcb200_knn_verify_euclid(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
                               const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
                               int64_t* votes, uint8_t* keep, void* stream);
-/* Same contract and the same (exact fp32) results, with the Q x S x D contraction on the tensor cores: TF32 scores straight
- * from the fp32 queries, a rigorous error bound selects a candidate superset per query, candidates are re-scored exactly.
- * Needs 64 <= S <= 4096, D % 8 == 0, and a device workspace of lvcb200_knn_tc_workspace(Q, S) bytes. */
-size_t lvcb200_knn_tc_workspace(int64_t Q, int S);
+/* Same contract and the same (exact fp32) results, with the Q x S x D contraction on the tensor cores.  Default path: queries and
+ * bank as bf16 hi/lo pairs, three-term product with fp32 accumulation in TMEM (scores good to 2e-5 |q|), the 12 best scores per
+ * query selected in the GEMM's epilogue; queries whose order is not certain at that accuracy are re-scored exactly on their 11
+ * candidates (or, if even the candidate set is uncertain, by the exact SIMT kernel).  LVCB200_KNN_TC=1 selects the round-1 path
+ * (TF32 scores from the fp32 queries, rigorous candidate superset, exact re-scoring of ~13 rows per query).
+ * Needs 64 <= S <= 4096, D % 8 == 0, and a device workspace of lvcb200_knn_tc_workspace(Q, S, D) bytes. */
+size_t lvcb200_knn_tc_workspace(int64_t Q, int S, int D);
+int lvcb200_knn_tc_select(int version /* 1 or 3; process-wide, for A/B measurements and tests */);
 int lvcb200_knn_verify_tc(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
                           const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
                           int64_t* votes, uint8_t* keep, void* workspace, size_t workspace_bytes, void* stream);

@@ -79,7 +79,8 @@ _SIGS = {
     "lvcb200_knn_prepare_euclid": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lvcb200_knn_verify_euclid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),
-    "lvcb200_knn_tc_workspace": (c_size_t, [c_int64, c_int]),
+    "lvcb200_knn_tc_select": (c_int, [c_int]),
+    "lvcb200_knn_tc_workspace": (c_size_t, [c_int64, c_int, c_int]),
     "lvcb200_knn_verify_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lvcb200_gemm_bf16": (c_int, [POINTER(GemmDesc), c_void_p]),

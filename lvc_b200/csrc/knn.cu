@@ -396,9 +396,18 @@ using namespace lvcb200;
 
 static inline int knn_s_pad(int S) { return (S + 7) / 8 * 8; }
 static inline int knn_s_al(int S) { return (S + 63) / 64 * 64; }
-// prepared layout: mean[D] | negc[S_al] | bhat[S_pad][D]
+// knn_tc3.cu: tensor-core path v2 (bf16 pair operands, top-k in the epilogue)
+int knn3_bank_rows(int S);
+size_t knn3_workspace_bytes(int64_t Q, int D);
+int knn3_split_bank(const float* bhat, int S, int D, const float* mean, void* bpair, float* mu2, cudaStream_t st);
+int knn3_verify(const float* mean, const float* negc, const float* bhat, const void* bpair, const float* mu2, const int64_t* bank_cls, int S,
+                int D, const float* queries, const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
+                int64_t* votes, uint8_t* keep, void* workspace, cudaStream_t st, int (*simt_fallback)(const uint8_t*, cudaStream_t, void*),
+                void* fb_ctx);
+// prepared layout: mean[D] | negc[S_al] | bhat[S_pad][D] | (256-byte aligned) mu2 | bank bf16 pair [2 * rows3][D]
+static inline size_t knn_f32_part(int S, int D) { return align_up(sizeof(float) * ((size_t)D + knn_s_al(S) + (size_t)knn_s_pad(S) * D), 256); }
 extern "C" size_t lvcb200_knn_prepared_bytes(int S, int D) {
-  return sizeof(float) * ((size_t)D + knn_s_al(S) + (size_t)knn_s_pad(S) * D);
+  return knn_f32_part(S, D) + 256 + (size_t)2 * knn3_bank_rows(S) * D * 2;
 }
 
 extern "C" int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_prepared, void* stream) {
@@ -412,7 +421,12 @@ extern "C" int lvcb200_knn_prepare(const float* bank, int S, int D, void* bank_p
   int rc = check_launch("knn_mean_kernel");
   if (rc) return rc;
   knn_normalize_kernel<<<knn_s_pad(S), 256, 0, s>>>(bank, S, D, mean, bhat, negc);
-  return check_launch("knn_normalize_kernel");
+  if ((rc = check_launch("knn_normalize_kernel"))) return rc;
+  if (D % 8 == 0) {   // operands of the tensor-core path: the normalised bank as a bf16 hi/lo pair, |mu|^2
+    uint8_t* tail = (uint8_t*)bank_prepared + knn_f32_part(S, D);
+    return knn3_split_bank(bhat, S, D, mean, tail + 256, (float*)tail, s);
+  }
+  return 0;
 }
 
 extern "C" int lvcb200_knn_prepare_euclid(const float* bank, int S, int D, void* bank_prepared, void* stream) {
@@ -453,9 +467,38 @@ extern "C" int lvcb200_knn_verify(const void* bank_prepared, const int64_t* bank
   return check_launch("knn_verify_kernel");
 }
 
-extern "C" size_t lvcb200_knn_tc_workspace(int64_t Q, int S) {
-  return align_up((size_t)Q * knn_s_pad(S) * 2, 256) + align_up((size_t)Q, 256);
+static int g_knn_tc_version = -1;
+static int knn_tc_version() {   // LVCB200_KNN_TC=1: the round-1 path (TF32 scores + per-query exact re-rank); default 3: bf16-pair scores, top-k in the epilogue
+  if (g_knn_tc_version < 0) {
+    const char* e = getenv("LVCB200_KNN_TC");
+    g_knn_tc_version = e ? atoi(e) : 3;
+  }
+  return g_knn_tc_version;
 }
+extern "C" int lvcb200_knn_tc_select(int version) {
+  LVC_REQUIRE(version == 1 || version == 3, "knn_tc_select: version must be 1 (TF32 + exact re-rank) or 3 (bf16 pairs, top-k in the epilogue)");
+  g_knn_tc_version = version;
+  return 0;
+}
+
+extern "C" size_t lvcb200_knn_tc_workspace(int64_t Q, int S, int D) {
+  const size_t v1 = align_up((size_t)Q * knn_s_pad(S) * 2, 256) + align_up((size_t)Q, 256);
+  const size_t v3 = knn3_workspace_bytes(Q, D);
+  return v1 > v3 ? v1 : v3;
+}
+
+namespace {
+struct SimtFallbackCtx {
+  const float* mean; const float* bhat; const int64_t* bank_cls; int S, D; const float* queries; const int64_t* query_cls; int64_t Q;
+  int topk, knn; int64_t* top_idx; float* top_sim; int64_t* votes; uint8_t* keep;
+};
+int simt_fallback_launch(const uint8_t* overflow, cudaStream_t st, void* vctx) {
+  const SimtFallbackCtx& c = *(const SimtFallbackCtx*)vctx;
+  knn_verify_kernel<<<(unsigned)ceil_div64(c.Q, QT), 256, 0, st>>>(c.mean, c.bhat, c.bank_cls, c.S, c.D, c.queries, c.query_cls, c.Q, c.topk, c.knn,
+                                                                   c.top_idx, c.top_sim, c.votes, c.keep, overflow);
+  return check_launch("knn_verify_kernel");
+}
+}  // namespace
 
 extern "C" int lvcb200_knn_verify_tc(const void* bank_prepared, const int64_t* bank_cls, int S, int D, const float* queries,
                                      const int64_t* query_cls, int64_t Q, int topk, int knn, int64_t* top_idx, float* top_sim,
@@ -465,12 +508,18 @@ extern "C" int lvcb200_knn_verify_tc(const void* bank_prepared, const int64_t* b
   if (Q == 0) return 0;
   LVC_REQUIRE(bank_prepared && bank_cls && queries && query_cls && top_idx && votes && keep && workspace, "knn_verify_tc: NULL pointer");
   LVC_REQUIRE(((uintptr_t)queries % 16) == 0, "knn_verify_tc: queries must be 16-byte aligned");
-  if (workspace_bytes < lvcb200_knn_tc_workspace(Q, S)) return set_error(LVCB200_EWORKSPACE, "knn_verify_tc: workspace too small");
+  if (workspace_bytes < lvcb200_knn_tc_workspace(Q, S, D)) return set_error(LVCB200_EWORKSPACE, "knn_verify_tc: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int S_pad = knn_s_pad(S);
   const float* mean = (const float*)bank_prepared;
   const float* negc = mean + D;
   const float* bhat = negc + knn_s_al(S);
+  if (knn_tc_version() >= 3 && topk <= 10 && D >= 64) {
+    const uint8_t* tail = (const uint8_t*)bank_prepared + knn_f32_part(S, D);
+    SimtFallbackCtx ctx{mean, bhat, bank_cls, S, D, queries, query_cls, Q, topk, knn, top_idx, top_sim, votes, keep};
+    return knn3_verify(mean, negc, bhat, tail + 256, (const float*)tail, bank_cls, S, D, queries, query_cls, Q, topk, knn, top_idx, top_sim, votes,
+                       keep, workspace, st, simt_fallback_launch, &ctx);
+  }
   __half* scores = (__half*)workspace;
   uint8_t* overflow = (uint8_t*)workspace + align_up((size_t)Q * S_pad * 2, 256);
   LVC_CUDA(cudaMemsetAsync(overflow, 0, (size_t)Q, st));

@@ -415,7 +415,8 @@ class KnnBank:
         return self.cosine and 64 <= self.S <= 4096 and self.D % 8 == 0 and 32 <= self.D <= 4096
 
     def verify(self, queries, query_cls, topk=10, knn=10, return_sim=False, path="auto"):
-        """path: "auto" (tensor-core scores + exact re-rank when the bank shape allows it), "tc", or "simt" (exact fp32 FMA)."""
+        """path: "auto" (tensor-core path when the bank shape allows it), "tc" / "tc3" (bf16-pair scores, top-k in the GEMM epilogue,
+        exact re-scoring of uncertain queries), "tc1" (round-1 path: TF32 scores + exact re-rank), or "simt" (exact fp32 FMA)."""
         _lib.require_cuda(queries, query_cls)
         q = queries.detach().to(torch.float32).contiguous()
         qc = query_cls.detach().to(torch.int64).contiguous()
@@ -426,9 +427,13 @@ class KnnBank:
         keep = torch.empty(Q, dtype=torch.uint8, device=dev)
         sim = torch.empty((Q, topk), dtype=torch.float32, device=dev) if return_sim else None
         lib = _lib.load()
-        use_tc = path == "tc" or (path == "auto" and self.tc_eligible() and Q > 0)
+        use_tc = path in ("tc", "tc1", "tc3") or (path == "auto" and self.tc_eligible() and Q > 0)
         if use_tc:
-            ws = _workspace("knn", lib.lvcb200_knn_tc_workspace(Q, self.S), dev)
+            if path in ("tc1", "tc3"):     # explicit version (A/B, tests): 1 = TF32 scores + exact re-rank, 3 = bf16 pairs + epilogue top-k
+                _lib.check(lib.lvcb200_knn_tc_select(int(path[2])), "lvcb200_knn_tc_select")
+            elif path == "tc":
+                _lib.check(lib.lvcb200_knn_tc_select(3), "lvcb200_knn_tc_select")
+            ws = _workspace("knn", lib.lvcb200_knn_tc_workspace(Q, self.S, self.D), dev)
             rc = lib.lvcb200_knn_verify_tc(_lib.ptr(self.prepared), _lib.ptr(self.cls), self.S, self.D, _lib.ptr(q), _lib.ptr(qc), Q,
                                            topk, knn, _lib.ptr(top_idx), _lib.ptr(sim), _lib.ptr(votes), _lib.ptr(keep), _lib.ptr(ws),
                                            ws.numel(), _lib.stream_ptr())

@@ -308,7 +308,7 @@ def test_knn_vs_oracle_tie_aware():
     q = rng.standard_normal((Q, D)).astype(np.float32) + means[qc] + 3.0
     want = O.knn_verify(bank, cls, q, qc)
     kb = ops.KnnBank(cu(bank), cu(cls))
-    for path in ("simt", "tc"):     # exact fp32 FMA kernel; tensor-core (TF32 scores + rigorous candidates + exact re-rank)
+    for path in ("simt", "tc3", "tc1"):     # exact fp32 FMA kernel; tensor-core v2 (bf16 pairs, epilogue top-k); v1 (TF32 + exact re-rank)
         got = kb.verify(cu(q), cu(qc), return_sim=True, path=path)
         gi, gs = got["top_idx"].cpu().numpy(), got["top_sim"].cpu().numpy()
         np.testing.assert_allclose(gs, want["top_sim"], rtol=1e-3, atol=2e-6)
@@ -319,9 +319,23 @@ def test_knn_vs_oracle_tie_aware():
         assert np.array_equal(got["keep"].cpu().numpy()[~rows_bad], want["keep"][~rows_bad]), path
     # candidate-set overflow (all bank rows identical -> every score ties) must fall back to the exact kernel, not fail
     same = np.repeat(bank[:1], 128, 0) + np.arange(128, dtype=np.float32)[:, None] * 0     # 128 identical rows
-    r_tc = ops.KnnBank(cu(same), cu(cls[:128])).verify(cu(q[:64]), cu(qc[:64]), path="tc")
     r_si = ops.KnnBank(cu(same), cu(cls[:128])).verify(cu(q[:64]), cu(qc[:64]), path="simt")
-    assert torch.equal(r_tc["keep"], r_si["keep"]) and torch.equal(r_tc["votes"], r_si["votes"])
+    for path in ("tc3", "tc1"):
+        r_tc = ops.KnnBank(cu(same), cu(cls[:128])).verify(cu(q[:64]), cu(qc[:64]), path=path)
+        assert torch.equal(r_tc["keep"], r_si["keep"]) and torch.equal(r_tc["votes"], r_si["votes"]), path
+    # DINO-shaped descriptors (384-d, 80 x 30 bank), a ragged query count and a bank that is not a multiple of the chunk size
+    S2, D2, Q2 = 2400 - 7, 384, 1000 + 13
+    cls2 = (np.arange(S2) % 80).astype(np.int64)
+    bank2 = rng.standard_normal((S2, D2)).astype(np.float32) + 0.5
+    q2 = rng.standard_normal((Q2, D2)).astype(np.float32) + 0.5
+    qc2 = rng.integers(0, 80, Q2).astype(np.int64)
+    w2 = O.knn_verify(bank2, cls2, q2, qc2)
+    for path in ("tc3", "tc1"):
+        g2 = ops.KnnBank(cu(bank2), cu(cls2)).verify(cu(q2), cu(qc2), return_sim=True, path=path)
+        gi, gs = g2["top_idx"].cpu().numpy(), g2["top_sim"].cpu().numpy()
+        np.testing.assert_allclose(gs, w2["top_sim"], rtol=1e-3, atol=2e-6)
+        bad = gi != w2["top_idx"]
+        assert bad.mean() < 2e-3 and np.all(np.abs(gs[bad] - w2["top_sim"][bad]) < 1e-5), path
     # ragged / tiny inputs
     r1 = ops.KnnBank(cu(bank[:37]), cu(cls[:37])).verify(cu(q[:5]), cu(qc[:5]), topk=10, knn=5)
     w1 = O.knn_verify(bank[:37], cls[:37], q[:5], qc[:5], topk=10, knn=5)
