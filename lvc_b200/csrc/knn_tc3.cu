@@ -6,12 +6,12 @@
 //       pair by knn_prepare) is swept in chunks of 160 rows: per 64-wide K block the three products q_hi b_hi + q_lo b_hi +
 //       q_hi b_lo accumulate in one fp32 TMEM tile (tcgen05.mma kind::f16, operands by TMA, 3-stage mbarrier ring); two TMEM
 //       buffers let the epilogue of chunk i overlap the MMAs of chunk i+1.  Epilogue: one thread per query reads its 160 scores
-//       (tcgen05.ld), adds -mu . bhat_s, and keeps the 12 best (score, index) keys in registers across the chunks.
+//       (tcgen05.ld), adds -mu . bhat_s, and keeps the 14 best (score, index) entries in registers across the chunks.
 //       Error of a score: operand representation 3 * 2^-18 |q| (rigorous, Cauchy-Schwarz, |bhat| = 1) + fp32 accumulation in
-//       the tensor core; eps = 2e-5 |q| covers both with a wide margin.  If all gaps among the 11 best exceed 2 eps the order
+//       the tensor core; eps = 2e-5 |q| covers both with a wide margin.  If all gaps that matter among the 14 best exceed 2 eps the order
 //       is certain and the thread writes top_idx / votes / mode / keep itself.  Otherwise the query is flagged:
-//   knn_resolve_kernel       : warp per flagged query, EXACT fp32 re-scoring of its 11 candidates (they contain the true top-10
-//       whenever the 12th approximate score is more than 2 eps below the 10th; if not, the query goes to the exact SIMT kernel).
+//   knn_resolve_kernel       : warp per flagged query, EXACT fp32 re-scoring of the uncertain ones among its 13 candidates (they contain the true top-10
+//       whenever the 14th approximate score is more than 2 eps below the 10th; if not, the query goes to the exact SIMT kernel).
 // The results are the exact-fp32 top-k of the SIMT kernel (same tie rule: lower bank index first).
 #include <cuda_fp16.h>
 #include <string.h>
@@ -25,7 +25,7 @@ constexpr int K3_STAGES = 3;
 constexpr int K3_STAGE_A = BLOCK_M * BLOCK_K * 2;          // 16 KB (one of hi / lo)
 constexpr int K3_STAGE_B = K3_CN * BLOCK_K * 2;            // 20 KB
 constexpr int K3_STAGE = 2 * K3_STAGE_A + 2 * K3_STAGE_B;  // 72 KB
-constexpr int K3_LIST = 12;
+constexpr int K3_LIST = 14;             // best (score, index) entries kept per query: top-10 + 3 boundary candidates + 1 sentinel
 constexpr int K3_THREADS = 256;
 constexpr int K3_SMEM = K3_STAGES * K3_STAGE + 1024 /*ctrl*/ + 1024 /*align*/;
 
@@ -93,22 +93,25 @@ struct Knn3Params {
   const float* negc; const float* qn2; const float* qmu; const float* mu2;
   const int64_t* bank_cls; const int64_t* query_cls;
   int64_t* top_idx; float* top_sim; int64_t* votes; uint8_t* keep;
-  int32_t* cand; uint8_t* flag;      // [Q, 11] candidate rows and 0 = done / 1 = resolve exactly / 2 = exact SIMT fallback
+  int32_t* nflag; int32_t* flist;                              // compact list of the flagged queries (the resolve kernel runs dense warps)
+  int32_t* cand; float* csc; uint16_t* amask; uint8_t* flag;   // per flagged query: 11 candidate rows, their approximate scores, which of them
+                                                               // sit in an uncertain cluster; flag 0 = done / 1 = re-score the clusters / 2 = exact full scan
 };
 
-__device__ __forceinline__ void k3_insert(unsigned long long (&t)[K3_LIST], unsigned long long key) {
-  if (key <= t[K3_LIST - 1]) return;
-  t[K3_LIST - 1] = key;
+// Sorted insertion into the per-query list (score as order-preserving uint32, bank row).  Bank rows reach a thread in ascending order,
+// so a strict comparison on the score alone leaves an equal score behind the earlier (lower) row: exactly the reference's tie rule.
+__device__ __forceinline__ void k3_insert(uint32_t (&ts)[K3_LIST], int (&ti)[K3_LIST], uint32_t key, int idx) {
+  if (key <= ts[K3_LIST - 1]) return;
+  ts[K3_LIST - 1] = key; ti[K3_LIST - 1] = idx;
 #pragma unroll
   for (int i = K3_LIST - 1; i > 0; i--) {
-    const unsigned long long a = t[i - 1], b = t[i];
+    const uint32_t a = ts[i - 1], b = ts[i];
+    const int ia = ti[i - 1], ib = ti[i];
     const bool sw = b > a;
-    t[i - 1] = sw ? b : a;
-    t[i] = sw ? a : b;
+    ts[i - 1] = sw ? b : a; ts[i] = sw ? a : b;
+    ti[i - 1] = sw ? ib : ia; ti[i] = sw ? ia : ib;
   }
 }
-__device__ __forceinline__ float k3_score(unsigned long long key) { return ordered_to_float((uint32_t)(key >> 32)); }
-__device__ __forceinline__ int k3_index(unsigned long long key) { return (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull)); }
 
 __global__ void __launch_bounds__(K3_THREADS, 1)
 knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b, const Knn3Params p) {
@@ -191,9 +194,9 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t cc = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       const int64_t q = (int64_t)tile * BLOCK_M + qd * 32 + lane;
-      unsigned long long top[K3_LIST];
+      uint32_t ts[K3_LIST]; int ti[K3_LIST];
 #pragma unroll
-      for (int i = 0; i < K3_LIST; i++) top[i] = 0ull;
+      for (int i = 0; i < K3_LIST; i++) { ts[i] = 0u; ti[i] = -1; }
       for (int c = 0; c < n_chunks; c++, cc++) {
         const uint32_t b = cc & 1u, bph = (cc >> 1) & 1u;
         const int s0 = c * K3_CN;
@@ -207,13 +210,22 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
+          // two phases, because every thread owns a different query: (1) branch-free, which of my 32 scores beat my current 12th best;
+          // (2) insert only those.  A per-element `if (beats) insert` makes the whole warp walk the 90-instruction insertion whenever
+          // ANY of its 32 queries accepts the element -- which is nearly always (first version: 352 M instructions, tensor pipe 29 %).
+          const uint32_t kth = ts[K3_LIST - 1];
+          uint32_t mask = 0u;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const int s = s0 + c0 + j;
-            if (c0 + j < n_here) {
-              const float sc = __fadd_rn(__uint_as_float(v[j]), __ldg(p.negc + s));
-              k3_insert(top, ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)s));
-            }
+            const int sj = s0 + c0 + j < p.S ? s0 + c0 + j : p.S - 1;
+            const uint32_t o = float_to_ordered(__fadd_rn(__uint_as_float(v[j]), __ldg(p.negc + sj)));
+            v[j] = o;
+            mask |= (uint32_t)(c0 + j < n_here && o > kth) << j;
+          }
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            k3_insert(ts, ti, v[j], s0 + c0 + j);
           }
         }
         tc_fence_before();
@@ -227,19 +239,26 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const int topk = p.topk;
       float sc[K3_LIST];
 #pragma unroll
-      for (int i = 0; i < K3_LIST; i++) sc[i] = k3_score(top[i]);
+      for (int i = 0; i < K3_LIST; i++) sc[i] = ordered_to_float(ts[i]);
       int state = 0;
       const int avail = p.S < K3_LIST ? p.S : K3_LIST;              // list entries that are real rows
-      if (avail > topk + 1 && sc[topk + 1] >= sc[topk - 1] - eps2) state = 2;   // the 12th could belong to the top-10: exact SIMT fallback
-      else {
+      // candidates that sit in a cluster of scores closer than 2 eps which reaches into the top-k: only these need exact scores
+      uint32_t am = 0u;
 #pragma unroll
-        for (int i = 0; i < K3_LIST - 2; i++)
-          if (i < topk && i + 1 < avail && sc[i] - sc[i + 1] < eps2) state = 1;
-      }
+      for (int i = 0; i < K3_LIST - 2; i++)
+        if (i + 1 < avail && sc[i] - sc[i + 1] < eps2 && (i < topk || ((am >> i) & 1u))) am |= 3u << i;
+      if (am) state = 1;
+      // the true top-k lies within {approx >= k-th approx - 2 eps}; if even the last list entry is that close the list may miss a member
+      if (avail == K3_LIST && sc[K3_LIST - 1] >= sc[topk - 1] - eps2) state = 2;
       if (state != 0) {
         p.flag[q] = (uint8_t)state;
+        p.flist[atomicAdd(p.nflag, 1)] = (int32_t)q;
+        p.amask[q] = (uint16_t)am;
 #pragma unroll
-        for (int i = 0; i < K3_LIST - 1; i++) p.cand[q * (K3_LIST - 1) + i] = i < avail ? k3_index(top[i]) : -1;
+        for (int i = 0; i < K3_LIST - 1; i++) {
+          p.cand[q * (K3_LIST - 1) + i] = i < avail ? ti[i] : -1;
+          p.csc[q * (K3_LIST - 1) + i] = sc[i];
+        }
         continue;
       }
       const float ncq2 = p.qn2[q] - 2.f * p.qmu[q] + *p.mu2;        // |q - mu|^2
@@ -249,7 +268,7 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
       for (int i = 0; i < K3_LIST; i++) {
         if (i < topk) {
-          const int idx = k3_index(top[i]);
+          const int idx = ti[i];
           vt[i] = p.bank_cls[idx];
           p.top_idx[q * topk + i] = idx;
           p.votes[q * topk + i] = vt[i];
@@ -274,52 +293,103 @@ knn_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// warp per query with flag == 1: exact fp32 centred-cosine scores of its 11 candidates, then top-k / votes / mode / keep
+// warp per flagged query.  flag 1: exact fp32 centred dot products for the candidates inside uncertain clusters (amask); the others
+// keep their approximate score -- clusters are separated by more than 2 eps, so sorting the mixed values gives the exact order.
+// flag 2 (the candidate set itself is uncertain, ~5e-4 of the queries): exact scan of the whole bank by the warp.
 __global__ void __launch_bounds__(256)
 knn_resolve_kernel(const float* __restrict__ mean, const float* __restrict__ bhat, const int64_t* __restrict__ bank_cls, int S, int D,
                    const float* __restrict__ queries, const int64_t* __restrict__ query_cls, int64_t Q, const int32_t* __restrict__ cand,
-                   const uint8_t* __restrict__ flag, int topk, int knn, int64_t* __restrict__ top_idx, float* __restrict__ top_sim,
-                   int64_t* __restrict__ votes, uint8_t* __restrict__ keep) {
+                   const float* __restrict__ csc, const uint16_t* __restrict__ amask, const uint8_t* __restrict__ flag,
+                   const int32_t* __restrict__ nflag, const int32_t* __restrict__ flist, int topk, int knn,
+                   int64_t* __restrict__ top_idx, float* __restrict__ top_sim, int64_t* __restrict__ votes, uint8_t* __restrict__ keep) {
   constexpr int NC = K3_LIST - 1;
-  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (q >= Q || flag[q] != 1) return;
-  int ci[NC];
-#pragma unroll
-  for (int j = 0; j < NC; j++) ci[j] = cand[q * NC + j];
-  float dot[NC];
-#pragma unroll
-  for (int j = 0; j < NC; j++) dot[j] = 0.f;
+  extern __shared__ float rs_q[];                      // [8 warps][D] centred queries
+  const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  if (slot >= Q || slot >= *nflag) return;
+  const int64_t q = flist[slot];
+  const int state = flag[q];
+  float* qc = rs_q + (size_t)wib * D;
   float nqc = 0.f;
-  for (int k = lane * 4; k < D; k += 128) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(queries + q * D + k));
-    const float4 m = __ldg(reinterpret_cast<const float4*>(mean + k));
-    v.x = __fsub_rn(v.x, m.x); v.y = __fsub_rn(v.y, m.y); v.z = __fsub_rn(v.z, m.z); v.w = __fsub_rn(v.w, m.w);
-    nqc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  for (int k0 = 0; k0 < D; k0 += 1024) {               // 8 independent 16-byte loads in flight per lane
+    float4 v[8];
 #pragma unroll
-    for (int j = 0; j < NC; j++) {
-      if (ci[j] < 0) continue;
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bhat + (size_t)ci[j] * D + k));
-      dot[j] += v.x * b.x + v.y * b.y + v.z * b.z + v.w * b.w;
+    for (int u = 0; u < 8; u++) {
+      const int k = k0 + u * 128 + lane * 4;
+      v[u] = k < D ? __ldg(reinterpret_cast<const float4*>(queries + q * D + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int k = k0 + u * 128 + lane * 4;
+      if (k < D) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mean + k));
+        float4 w = v[u];
+        w.x = __fsub_rn(w.x, m.x); w.y = __fsub_rn(w.y, m.y); w.z = __fsub_rn(w.z, m.z); w.w = __fsub_rn(w.w, m.w);
+        nqc += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
+        *reinterpret_cast<float4*>(qc + k) = w;
+      }
     }
   }
-  for (int o = 16; o; o >>= 1) {
-    nqc += __shfl_xor_sync(0xffffffffu, nqc, o);
-#pragma unroll
-    for (int j = 0; j < NC; j++) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
-  }
+  for (int o = 16; o; o >>= 1) nqc += __shfl_xor_sync(0xffffffffu, nqc, o);
   const float nrm = sqrtf(nqc);
   const float inv_n = 1.0f / (nrm > 1e-8f ? nrm : 1e-8f);
-  // lane j holds candidate j; rank by (sim desc, index asc)
-  float mv = -INFINITY; int mi = 0x7fffffff;
+  __syncwarp();
+  auto exact_dot = [&](int row) {                      // all lanes return the full sum
+    const float* br = bhat + (size_t)row * D;
+    float d = 0.f;
+    for (int k0 = 0; k0 < D; k0 += 1024) {
+      float4 b[8];
 #pragma unroll
-  for (int j = 0; j < NC; j++) if (lane == j && ci[j] >= 0) { mv = dot[j] * inv_n; mi = ci[j]; }
+      for (int u = 0; u < 8; u++) {
+        const int k = k0 + u * 128 + lane * 4;
+        b[u] = k < D ? __ldg(reinterpret_cast<const float4*>(br + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int k = k0 + u * 128 + lane * 4;
+        if (k < D) {
+          const float4 a = *reinterpret_cast<const float4*>(qc + k);
+          d += a.x * b[u].x + a.y * b[u].y + a.z * b[u].z + a.w * b[u].w;
+        }
+      }
+    }
+    for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    return d;
+  };
+  float mv = -INFINITY; int mi = 0x7fffffff;           // lane j: value and bank row of list entry j (sorted or not)
+  int n_list = 0;
+  if (state == 1) {
+    const uint32_t am = amask[q];
+    if (lane < NC) { mi = cand[q * NC + lane]; if (mi < 0) mi = 0x7fffffff; else mv = csc[q * NC + lane] * inv_n; }
+    for (int j = 0; j < NC; j++) {
+      if (!((am >> j) & 1u)) continue;                 // uniform across the warp
+      const int row = __shfl_sync(0xffffffffu, mi, j);
+      if (row == 0x7fffffff) continue;
+      const float d = exact_dot(row) * inv_n;
+      if (lane == j) mv = d;
+    }
+    n_list = NC;
+  } else {
+    // exact scan: lane r (< topk) holds the r-th best so far
+    for (int s0 = 0; s0 < S; s0++) {
+      const float d = exact_dot(s0) * inv_n;
+      const bool mine_worse = lane < topk && (d > mv || (d == mv && s0 < mi));     // the new entry ranks before this lane's entry
+      const unsigned int w = __ballot_sync(0xffffffffu, mine_worse);
+      if (w) {
+        const int pos = __ffs(w) - 1;                  // insertion position: entries at pos.. shift down by one
+        const float uv = __shfl_up_sync(0xffffffffu, mv, 1); const int ui = __shfl_up_sync(0xffffffffu, mi, 1);
+        if (lane > pos && lane < topk) { mv = uv; mi = ui; }
+        if (lane == pos) { mv = d; mi = s0; }
+      }
+    }
+    n_list = topk;
+  }
   int rank = 0;
-  for (int o = 0; o < NC; o++) {
+  for (int o = 0; o < n_list; o++) {
     const float ov = __shfl_sync(0xffffffffu, mv, o); const int oi = __shfl_sync(0xffffffffu, mi, o);
     rank += (ov > mv) || (ov == mv && oi < mi);
   }
-  const bool out_lane = lane < NC && mi != 0x7fffffff && rank < topk;
+  const bool out_lane = lane < n_list && mi != 0x7fffffff && rank < topk;
   const int64_t vote = out_lane ? bank_cls[mi] : -1;
   if (out_lane) {
     top_idx[q * topk + rank] = mi;
@@ -343,11 +413,6 @@ knn_resolve_kernel(const float* __restrict__ mean, const float* __restrict__ bha
   if (lane == 0) keep[q] = (query_cls[q] == bvv) ? 1 : 0;
 }
 
-__global__ void knn_flag_to_overflow_kernel(const uint8_t* __restrict__ flag, int64_t Q, uint8_t* __restrict__ overflow) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Q) overflow[i] = flag[i] == 2 ? 1 : 0;
-}
-
 }  // namespace lvcb200
 
 using namespace lvcb200;
@@ -357,8 +422,8 @@ int knn3_bank_rows(int S) { return (S + K3_CN - 1) / K3_CN * K3_CN; }
 
 size_t knn3_workspace_bytes(int64_t Q, int D) {
   const int64_t Sq = (Q + 127) / 128 * 128;
-  return align_up((size_t)2 * Sq * D * 2, 256) + 2 * align_up((size_t)Q * 4, 256) + align_up((size_t)Q * (K3_LIST - 1) * 4, 256) +
-         2 * align_up((size_t)Q, 256);
+  return align_up((size_t)2 * Sq * D * 2, 256) + 2 * align_up((size_t)Q * 4, 256) + 2 * align_up((size_t)Q * (K3_LIST - 1) * 4, 256) +
+         align_up((size_t)Q * 2, 256) + align_up((size_t)Q, 256) + 256 + align_up((size_t)Q * 4, 256);
 }
 
 int knn3_split_bank(const float* bhat, int S, int D, const float* mean, void* bpair, float* mu2, cudaStream_t st) {
@@ -378,9 +443,12 @@ int knn3_verify(const float* mean, const float* negc, const float* bhat, const v
   float* qn2 = (float*)ws; ws += align_up((size_t)Q * 4, 256);
   float* qmu = (float*)ws; ws += align_up((size_t)Q * 4, 256);
   int32_t* cand = (int32_t*)ws; ws += align_up((size_t)Q * (K3_LIST - 1) * 4, 256);
+  float* csc = (float*)ws; ws += align_up((size_t)Q * (K3_LIST - 1) * 4, 256);
+  uint16_t* amask = (uint16_t*)ws; ws += align_up((size_t)Q * 2, 256);
   uint8_t* flag = ws; ws += align_up((size_t)Q, 256);
-  uint8_t* overflow = ws;
-  LVC_CUDA(cudaMemsetAsync(flag, 0, (size_t)Q, st));
+  int32_t* nflag = (int32_t*)ws; ws += 256;
+  int32_t* flist = (int32_t*)ws;
+  LVC_CUDA(cudaMemsetAsync(flag, 0, align_up((size_t)Q, 256) + 256, st));   // flags and the list counter
   knn_split_queries_kernel<<<(unsigned)ceil_div64(Q * 32, 256), 256, 0, st>>>(queries, Q, D, mean, qpair, Sq, qn2, qmu);
   int rc = check_launch("knn_split_queries_kernel");
   if (rc) return rc;
@@ -396,7 +464,7 @@ int knn3_verify(const float* mean, const float* negc, const float* bhat, const v
   p.negc = negc; p.qn2 = qn2; p.qmu = qmu; p.mu2 = mu2;
   p.bank_cls = bank_cls; p.query_cls = query_cls;
   p.top_idx = top_idx; p.top_sim = top_sim; p.votes = votes; p.keep = keep;
-  p.cand = cand; p.flag = flag;
+  p.cand = cand; p.csc = csc; p.amask = amask; p.flag = flag; p.nflag = nflag; p.flist = flist;
   static bool attr_set = false;
   if (!attr_set) {
     LVC_CUDA(cudaFuncSetAttribute(knn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM));
@@ -405,10 +473,14 @@ int knn3_verify(const float* mean, const float* negc, const float* bhat, const v
   const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;
   knn_tc3_kernel<<<grid, K3_THREADS, K3_SMEM, st>>>(tq, tb, p);
   if ((rc = check_launch("knn_tc3_kernel"))) return rc;
-  knn_resolve_kernel<<<(unsigned)ceil_div64(Q * 32, 256), 256, 0, st>>>(mean, bhat, bank_cls, S, D, queries, query_cls, Q, cand, flag, topk, knn,
-                                                                       top_idx, top_sim, votes, keep);
-  if ((rc = check_launch("knn_resolve_kernel"))) return rc;
-  knn_flag_to_overflow_kernel<<<(unsigned)ceil_div64(Q, 256), 256, 0, st>>>(flag, Q, overflow);
-  if ((rc = check_launch("knn_flag_to_overflow_kernel"))) return rc;
-  return simt_fallback(overflow, st, fb_ctx);
+  const size_t rs_smem = (size_t)8 * D * sizeof(float);
+  static size_t rs_set = 0;
+  if (rs_smem > rs_set && rs_smem > 48 * 1024) {
+    LVC_CUDA(cudaFuncSetAttribute(knn_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    rs_set = rs_smem;
+  }
+  knn_resolve_kernel<<<(unsigned)ceil_div64(Q * 32, 256), 256, rs_smem, st>>>(mean, bhat, bank_cls, S, D, queries, query_cls, Q, cand, csc, amask, flag,
+                                                                             nflag, flist, topk, knn, top_idx, top_sim, votes, keep);
+  (void)simt_fallback; (void)fb_ctx;   // the uncertain-candidate-set case is an exact scan inside knn_resolve_kernel
+  return check_launch("knn_resolve_kernel");
 }
