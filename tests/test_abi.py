@@ -36,7 +36,7 @@ def test_abi_version_and_error_channel():
     assert lib.lvcb200_batched_nms_workspace(1000) > 1000 * 20
     # mean | -c_s (padded) | bhat | |mu|^2 | the normalised bank as a bf16 hi/lo pair (rows padded to the 160-row chunk of the v2 kernel)
     assert lib.lvcb200_knn_prepared_bytes(600, 1024) == 4 * (1024 + 640 + 600 * 1024) + 256 + 2 * 640 * 1024 * 2
-    assert lib.lvcb200_knn_tc_workspace(200_000, 600, 1024) >= 2 * 200_064 * 1024 * 2
+    assert lib.lvcb200_knn_tc_workspace(200_000, 600, 1024) >= 2 * 200_064 * 1024 * 2      # the queries as a bf16 hi/lo pair
 
 
 def test_no_cpu_fallback():
