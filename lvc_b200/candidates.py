@@ -19,7 +19,11 @@ def select_candidates(image_id: torch.Tensor, category: torch.Tensor, score: tor
     box-area / image-area ratio), ``--full`` (mark the other same-class detections of the kept images as ignore regions).
     Score mode keeps ``K_min < score <= K_max`` (the reference's left ``searchsorted`` on ``-scores``, :169-174); valid
     detections are those of a novel class on images that do NOT hold that class's few-shot ground truth (:133-134), with
-    ``0 < area < 1e10`` and ``ar < area / image_area < 1`` (:39-43, :136-137)."""
+    ``0 < area < 1e10`` and ``ar < area / image_area < 1`` (:39-43, :136-137).
+    One deliberate difference: with ``full`` and NO kept detection for a class the reference calls pycocotools'
+    ``getAnnIds(imgIds=[])``, which treats the empty list as "all images" and therefore marks every valid detection of that class as
+    an ignore region (:175-186); here (and in ``lvcb200_candidate_filter``) such a class yields nothing, which is what the
+    surrounding code intends ("the other detections of the images that hold a pseudo-label")."""
     dev = score.device
     n = score.shape[0]
     flags = torch.zeros(n, dtype=torch.int8, device=dev)

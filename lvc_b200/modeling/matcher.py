@@ -69,7 +69,9 @@ class Matcher:
 def rpn_losses(anchors, pred_objectness_logits, pred_anchor_deltas, gt_labels, gt_boxes, batch_size_per_image=256,
                box2box_weights=(1.0, 1.0, 1.0, 1.0), smooth_l1_beta=0.0, loss_weight=None):
     """RPN.losses (rpn.py:328-400), smooth-L1 flavour: anchors [A,4] (levels concatenated), logits [N,A], deltas [N,A,4], gt_labels [N,A]
-    (int8: -1 ignore / 0 / 1), gt_boxes [N,A,4] -> {"loss_rpn_cls", "loss_rpn_loc"} (0-d CUDA tensors)."""
+    (int8: -1 ignore / 0 / 1), gt_boxes [N,A,4] -> {"loss_rpn_cls", "loss_rpn_loc"} (0-d CUDA tensors).
+    FORWARD ONLY (loss values for evaluation / logging): inputs are detached and there is no backward kernel, so the result carries
+    no autograd graph -- training with it needs the dense backward passes, which are out of scope."""
     a = getattr(anchors, "tensor", anchors)
     _lib.require_cuda(a, pred_objectness_logits, pred_anchor_deltas, gt_labels, gt_boxes)
     a = a.detach().to(torch.float32).contiguous()
@@ -90,7 +92,8 @@ def rpn_losses(anchors, pred_objectness_logits, pred_anchor_deltas, gt_labels, g
 def fast_rcnn_losses(pred_class_logits, pred_proposal_deltas, gt_classes, proposal_boxes, gt_boxes, box2box_weights=(10.0, 10.0, 5.0, 5.0),
                      smooth_l1_beta=0.0, loss_weight=None):
     """FastRCNNOutputs.losses (lvc/modeling/roi_heads/fast_rcnn.py:424-438), smooth-L1 flavour: logits [R,K+1], deltas [R,4K] or [R,4],
-    gt_classes [R] (K = background), proposal / gt boxes [R,4] -> {"loss_cls", "loss_box_reg"} (0-d CUDA tensors, both divided by R)."""
+    gt_classes [R] (K = background), proposal / gt boxes [R,4] -> {"loss_cls", "loss_box_reg"} (0-d CUDA tensors, both divided by R).
+    FORWARD ONLY, like ``rpn_losses``: detached inputs, no backward kernel."""
     pb = getattr(proposal_boxes, "tensor", proposal_boxes)
     gb = getattr(gt_boxes, "tensor", gt_boxes)
     _lib.require_cuda(pred_class_logits, pred_proposal_deltas, gt_classes, pb, gb)

@@ -368,3 +368,66 @@ def test_edge_cases_tiny_image_and_no_detections():
     col = {}
     ref = OM.detector_forward(cfg2, sd, [im], device="cuda", collect=col, emulate_bf16=True)
     assert abs(c - len(col["proposals"][0][0])) <= 0.1 * c + 3
+
+
+def test_proposal_network_and_regonly_models():
+    """The other two meta-architectures of the mining path through their public API (rcnn.py:336-488).
+    ProposalNetwork: the proposals are those the detector's own RPN stage produces (bit-equal), rescaled like detector_postprocess.
+    GeneralizedRCNNRegOnly: gt_boxes regressed through the three cascade heads == BoxCorrectorHead on the same features, and within
+    0.5 px of the fp32 oracle's box corrector on the oracle's own features."""
+    from lvc_b200.modeling import BoxCorrectorHead, GeneralizedRCNNRegOnly, ProposalNetwork
+    from lvc_b200.structures import Boxes, Instances
+    from lvc_b200.weights import synthetic_corrector_head
+    cfg = DetectorConfig(depth=50)
+    sd = synthetic_state_dict(cfg, 0)
+    ims = _images(31, [(192, 256), (160, 224)])
+    # --- ProposalNetwork
+    pn = ProposalNetwork(cfg, {k: v for k, v in sd.items() if not k.startswith("roi_heads.")}, use_cuda_graph=False)
+    out = pn([{"image": im, "height": 2 * im.shape[1], "width": 2 * im.shape[2]} for im in ims])
+    eng = DetectorEngine(cfg, sd)
+    eng.debug = {}
+    eng.run([im.cuda() for im in ims])
+    torch.cuda.synchronize()
+    for i, o in enumerate(out):
+        c = int(eng.debug["prop_counts"][i])
+        want = eng.debug["props"][i, :c].clone()
+        want[:, 0::2] *= 2.0
+        want[:, 1::2] *= 2.0
+        p = o["proposals"]
+        assert p.image_size == (2 * ims[i].shape[1], 2 * ims[i].shape[2]) and len(p) == c
+        assert torch.equal(p.proposal_boxes.tensor, want) and torch.equal(p.objectness_logits, eng.debug["prop_logits"][i, :c])
+    raw, sizes = pn([{"image": im} for im in ims], no_post=True)
+    assert len(raw) == 2 and sizes == [tuple(im.shape[-2:]) for im in ims]
+    # --- GeneralizedRCNNRegOnly
+    ccfg = DetectorConfig(depth=50, num_fc=3)
+    hsd = synthetic_corrector_head(ccfg, 3)
+    for k in list(hsd):
+        if "bbox_pred.weight" in k:
+            hsd[k] = hsd[k] * 30                      # visible corrections
+    full = {k: v for k, v in sd.items() if not k.startswith("roi_heads.")}
+    full.update(hsd)
+    model = GeneralizedRCNNRegOnly(ccfg, full)
+    rng = np.random.default_rng(5)
+    from lvc_b200.testing import coco_like_boxes
+    gts, inputs = [], []
+    for im in ims:
+        b = coco_like_boxes(rng, 20, W=im.shape[2], H=im.shape[1], min_side=8, max_side=150)
+        inst = Instances(tuple(im.shape[-2:]))
+        inst.gt_boxes = Boxes(torch.from_numpy(b))
+        inst.gt_classes = torch.from_numpy(rng.integers(0, 80, 20))
+        gts.append(b)
+        inputs.append({"image": im, "instances": inst, "height": im.shape[1], "width": im.shape[2]})
+    res = model(inputs)
+    assert len(res) == 2 and "image" not in res[0]
+    pyramid, _ = model.engine.run_features([im.cuda() for im in ims])
+    head = BoxCorrectorHead(ccfg, hsd)
+    want = head([pyramid[l] for l in (2, 3, 4, 5)], [torch.from_numpy(g).cuda() for g in gts], [tuple(im.shape[-2:]) for im in ims])
+    col = {}
+    OM.detector_forward(cfg, sd, ims, device="cuda", collect=col)
+    ref = OM.box_corrector_forward(ccfg, hsd, col["features"], gts, [np.zeros(20, np.int64)] * 2, [tuple(im.shape[-2:]) for im in ims])
+    for i, r in enumerate(res):
+        got = r["instances"].pred_boxes.tensor
+        keep = torch.ones(len(want[i]), dtype=torch.bool, device=want[i].device)      # the reference filters on the (non-empty) gt boxes
+        assert torch.equal(got.cuda(), want[i][keep]) and torch.equal(r["instances"].pred_classes, inputs[i]["instances"].gt_classes)
+        assert np.abs(got.numpy() - gts[i][keep.cpu().numpy()]).max() > 0.5          # the heads moved the boxes
+        assert np.abs(got.numpy() - ref[i][keep.cpu().numpy()]).max() < 0.5          # bf16 features / weights vs the fp32 oracle
