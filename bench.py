@@ -190,38 +190,65 @@ def knn_section(rank, world, dev, dist, with_cpu):
     qcls = torch.randint(0, ncls, (qh - ql,), generator=g2, device=dev)
     queries = torch.randn(qh - ql, D, generator=g2, device=dev) + means[qcls]
     res = {}
-    for path in ("tc", "tc1", "simt"):
-        times = []
-        for it in range(4):
+
+    def step(path):
+        c, b = all_gather_bank(cls_all[lo:hi], bank_all[lo:hi], total=S)  # the one exchange step: a single all_gather, no host sync
+        kb = ops.KnnBank(b, c)
+        return kb.verify(queries, qcls, topk=10, knn=10, path=path)
+
+    def timed(fn, reps):
+        times, r = [], None
+        for it in range(reps):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            c, b = all_gather_bank(cls_all[lo:hi], bank_all[lo:hi], total=S)  # the one exchange step: a single all_gather, no host sync
-            kb = ops.KnnBank(b, c)
-            out = kb.verify(queries, qcls, topk=10, knn=10, path=path)
+            r = fn()
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         t = torch.tensor([min(times[1:])], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-        alg_bytes = Q * D * 4 + S * D * 4 + Q * 10 * 8 + Q            # 837.9 MB
+        return float(t[0]), r
+
+    alg_bytes = Q * D * 4 + S * D * 4 + Q * 10 * 8 + Q            # 837.9 MB
+    for path in ("tc", "tc1", "simt"):
+        ms, out = timed(lambda: step(path), 4)
         res[path] = {"ms": ms, "queries_per_s": Q / (ms / 1e3), "hbm_gbs": alg_bytes / (ms / 1e3) / 1e9}
         if path == "tc":
             res["keep_fraction_rank0"] = float(out["keep"].float().mean())
-        if path == "simt" and world > 1:
-            pass
+    # the same stream-ordered sequence (all-gather of the bank -> prepare -> scores / top-k -> resolve) captured ONCE in a CUDA graph and
+    # replayed: with 25k queries per rank (8 GPUs) the eager number is dominated by ~30 host-side launches, not by the device
+    try:
+        if os.environ.get("LVCB200_BENCH_KNN_GRAPH", "1") != "0":
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step("tc")
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gout = step("tc")
+            ms_g, _ = timed(lambda: g.replay(), 5)
+            res["tc"]["graph_replay_ms"] = ms_g
+            res["tc"]["graph_replay_hbm_gbs"] = alg_bytes / (ms_g / 1e3) / 1e9
+            res["tc"]["graph_keep_fraction_rank0"] = float(gout["keep"].float().mean())
+    except Exception as e:  # noqa: BLE001
+        res["tc"]["graph_replay_error"] = repr(e)
     peak_tf, peak_hbm, which, _ = measured_peaks()
-    res["tc"]["kernels"] = "knn_split_queries (fp32 -> bf16 hi/lo pair) + knn_tc3 (tcgen05 3-term product, top-12 in the TMEM epilogue) + knn_resolve (exact re-scoring of uncertain queries)"
+    best_gbs = res["tc"].get("graph_replay_hbm_gbs", res["tc"]["hbm_gbs"])
+    res["tc"]["kernels"] = "knn_split_queries (fp32 -> bf16 hi/lo pair) + knn_tc3 (tcgen05 3-term product, top-14 in the TMEM epilogue) + knn_resolve (exact re-scoring of uncertain queries)"
     res["tc1"]["kernels"] = "round-1 path: gemm_bf16_tc_kernel kind::tf32 (fp16 score matrix) + knn_rerank (exact re-scoring of ~13 candidate rows per query)"
     out = {"workload": "200k x 1024 fp32 queries vs 600 x 1024 bank (20 classes x 30 shots), centred cosine top-10 + mode vote",
            "tensor_core_path": res["tc"], "tensor_core_path_v1": res["tc1"], "simt_exact_path": res["simt"],
-           "roofline": {"bound": "hbm", "achieved": res["tc"]["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s",
-                        "frac": res["tc"]["hbm_gbs"] / peak_hbm / world, "algorithmic_bytes": 837.9e6,
-                        "note": "includes the bank all-gather + bank preparation inside the timed region"},
+           "roofline": {"bound": "hbm", "achieved": best_gbs, "peak": peak_hbm, "unit": "GB/s",
+                        "frac": best_gbs / peak_hbm / world, "algorithmic_bytes": 837.9e6,
+                        "note": "whole-job GB/s over all ranks / (ranks x per-GPU peak); includes the bank all-gather + bank preparation inside the timed "
+                                "region; the CUDA-graph replay of the sequence when it was captured, else the eager launches"},
            "keep_fraction_rank0": res.get("keep_fraction_rank0")}
     if with_cpu and rank == 0:
         from oracle import oracle as O

@@ -64,7 +64,8 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
         dist.all_gather_into_tensor(out.view(world * (cap + 1), D + 2), pack, group=group)
     else:
         dist.all_gather(list(out.unbind(0)), pack, group=group)
-    all_gather_bank.last_check = (out[:, 0, 0] == torch.tensor(sizes, dtype=torch.float32, device=dev)).all()   # device flag, not synced
+    if not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):   # (a host list cannot be uploaded inside a CUDA-graph capture)
+        all_gather_bank.last_check = (out[:, 0, 0] == torch.tensor(sizes, dtype=torch.float32, device=dev)).all()   # device flag, not synced
     desc = torch.cat([out[r, 1:1 + sizes[r], :D] for r in range(world)])
     cls = torch.cat([out[r, 1:1 + sizes[r], D:].contiguous().view(torch.int64).view(-1) for r in range(world)])
     return cls, desc
