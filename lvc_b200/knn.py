@@ -55,7 +55,7 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
         cap = max(sizes)
     # one padded block carries the header, the descriptors and the (bit-cast) classes: a single collective on the data path
     pack = torch.zeros((cap + 1, D + 2), dtype=torch.float32, device=dev)
-    pack[0, 0] = float(n_mine)
+    pack[0, :1].fill_(float(n_mine))          # (a fill kernel: CUDA-graph capturable, unlike an element assignment from a host scalar)
     pack[1:1 + n_mine, :D] = shot_descriptors.float()
     if n_mine:
         pack[1:1 + n_mine, D:] = shot_classes.to(torch.int64).view(-1, 1).view(torch.float32).view(-1, 2)
