@@ -307,6 +307,21 @@ int lvcb200_make_rois(const float* proposals, const int32_t* counts, int n, int 
 int lvcb200_crops_qe(const void* image, int image_dtype, int H, int W, const int32_t* geom, int n, int S, const float* mean,
                      const float* inv_std, float* out, void* stream);
 
+/* "Next" row: the DINO ViT-S/8 forward between the crops and the kNN bank (tools/run_nearest_neighbours.py:108-128,
+ * 292-295: `crop_features = model(crops)`, model = torch.hub facebookresearch/dino:main `dino_vits8`, a dependency outside the reference
+ * tree; architecture restated from its published definition).  The linear layers run on lvcb200_gemm_bf16; these are the kernels between:
+ *   vit_patchify : crops [B,3,S,S] fp32 -> patch rows [B*(S/patch)^2, 3*patch*patch] bf16, columns in (c, iy, ix) order (= conv weight order)
+ *   vit_assemble : x[b, 0] = cls + pos[0]; x[b, 1 + i] = patch_tokens[b, i] + pos[1 + i]      (bf16 [B*(Np+1), D])
+ *   layernorm    : rows of bf16 x (row pitch ldx) -> (x - mean) * rstd * gamma + beta, bf16 or fp32 out (row pitch ldo), eps as given
+ *   gelu         : exact (erf) GELU in place over n bf16 values (n % 8 == 0)
+ *   attention    : qkv [B*N, 3*H*64] bf16 (q | k | v, each head-major) -> softmax(q k^T * scale) v, out [B*N, H*64] bf16; head_dim 64 */
+int lvcb200_vit_patchify(const float* crops, int B, int S, int patch, void* out, void* stream);
+int lvcb200_vit_assemble(const void* patch_tokens, const float* cls_token, const float* pos_embed, int B, int Np, int D, void* x, void* stream);
+int lvcb200_layernorm(const void* x, int64_t rows, int D, int64_t ldx, const float* gamma, const float* beta, float eps, void* out,
+                      int out_dtype, int64_t ldo, void* stream);
+int lvcb200_gelu(void* x, int64_t n, void* stream);
+int lvcb200_attention(const void* qkv, int B, int N, int H, int head_dim, float scale, void* out, void* stream);
+
 /* "Next" row: training-side users of the path's operators.
  * roi_align_backward: autograd backward of detectron2.layers.roi_align (ROIAlign_cuda.cu:141-306 RoIAlignBackwardFeature):
  *   grad_output [R,C,ph,pw] fp32, rois [R,5] -> grad_input [N,C,H,W] fp32 (zeroed here, then accumulated with RED.ADD).
