@@ -291,6 +291,38 @@ def corrector_section(dev):
             "tflops": flop / (ms / 1e3) / 1e12, "frac_of_peak": flop / (ms / 1e3) / 1e12 / peak_tf}
 
 
+def descriptor_section(dev):
+    """"Next" row f1: the label-verification front end -- 1 024 candidate boxes of one 800 x 1333 image -> context crops (224 x 224) ->
+    DINO ViT-S/8 (random-init weights of the hub model's shapes) -> 384-d descriptors, all on the device."""
+    from lvc_b200.knn import get_descriptors
+    from lvc_b200.modeling import DinoViT, synthetic_vit_state_dict
+    import numpy as np
+    from lvc_b200.testing import coco_like_boxes
+    model = DinoViT(synthetic_vit_state_dict(seed=0), dev)
+    img = (torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)) * 255).to(torch.uint8).to(dev)
+    nb = 1024
+    boxes = torch.from_numpy(coco_like_boxes(np.random.default_rng(1), nb).astype(np.int64))
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    for _ in range(2):
+        f = get_descriptors(model, img, boxes, mean, std)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        f = get_descriptors(model, img, boxes, mean, std)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    n_tok, d = 785, 384
+    lin = 12 * 2 * n_tok * (d * 3 * d + d * d + 2 * d * 4 * d) + 2 * 784 * 192 * d
+    att = 12 * 6 * 2 * 2 * n_tok * n_tok * 64
+    peak_tf, _, _, peak_burst = measured_peaks()
+    return {"workload": "1024 boxes of one 800x1333 uint8 image -> context crops 224x224 -> ViT-S/8 (12 blocks, 384-d, 785 tokens) -> descriptors",
+            "ms": ms, "crops_per_s": nb / (ms / 1e3), "gflop_per_crop": (lin + att) / 1e9,
+            "tflops": nb * (lin + att) / (ms / 1e3) / 1e12, "frac_of_burst_bf16_peak": nb * (lin + att) / (ms / 1e3) / 1e12 / peak_burst,
+            "descriptor_norm_mean": float(f.norm(dim=1).mean())}
+
+
 def ops_section(dev):
     """Op-level numbers for the HBM/latency-bound kernels on COCO-shaped synthetic boxes: achieved GB/s =
     algorithmic bytes / CUDA-event time of 10 back-to-back launches."""
@@ -674,6 +706,7 @@ def main():
             extras["mining_config3"] = {"error": repr(e)}
         if rank == 0 and world == 1:
             for name, fn in (("box_corrector", lambda: corrector_section(dev)), ("ops", lambda: ops_section(dev)),
+                             ("descriptor_front_end", lambda: descriptor_section(dev)),
                              ("parity", lambda: parity_block(dev_images, sd))):
                 try:
                     extras[name] = fn()

@@ -228,7 +228,7 @@ typedef struct {
   void* D; int64_t ldd; int d_dtype;            /* LVCB200_BF16, LVCB200_F16 or LVCB200_F32 */
   int64_t M; int N; int K;                      /* GEMM extents (K per tap), K % 64 == 0, N % 16 == 0 */
   int taps; int32_t shift[9];                   /* row shift per tap */
-  int relu;
+  int relu;                                     /* 0 none, 1 ReLU, 2 exact (erf) GELU (bf16 output, N > 128, no residual: the ViT MLP) */
   int plane_h, plane_w;                         /* 0 = no border masking */
   /* optional (appended; NULL = off): FPN top-down path fused into the lateral conv (fpn.py:128-134): D += nearest-2x-upsample(up),
    * up = the coarser level's zero-bordered bf16 plane [n, up_plane_h, up_plane_w, >= N] (row pitch ldu elements), this plane being

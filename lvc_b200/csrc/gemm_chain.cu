@@ -438,6 +438,7 @@ static int chain_validate(const lvcb200_gemm_desc* descs, int n, int* total_m_ti
     LVC_REQUIRE(d->N >= 64 && d->N % 64 == 0 && d->K >= 64 && d->K % 64 == 0, "gemm_chain: N and K must be multiples of 64");
     LVC_REQUIRE(d->taps >= 1 && d->taps <= 9, "gemm_chain: taps");
     LVC_REQUIRE(d->split_rows == 0, "gemm_chain: split (strict-mode) layers run as per-layer launches");
+    LVC_REQUIRE(d->relu == 0 || d->relu == 1, "gemm_chain: activation must be none or ReLU");
     LVC_REQUIRE(d->A && d->W && d->D, "gemm_chain: NULL pointer");
     LVC_REQUIRE(((uintptr_t)d->bias % 16) == 0, "gemm_chain: bias must be 16-byte aligned");
     LVC_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0 && d->ldd % 8 == 0 && (!d->residual || d->ldr % 8 == 0), "gemm_chain: leading dimensions must be multiples of 8");

@@ -72,7 +72,8 @@ constexpr int kTap3BytesA = 136 * 128;   // 17 KB: rows m0 + shift(kh, kw = 0) .
 // [2 * split_rows, cols] matrices with the hi half at row 0 and the lo half at row split_rows; W is [N, taps * 2K] with [hi | lo]
 // per tap.  The contraction is the classic three-term product A_hi W_hi + A_lo W_hi + A_hi W_lo (the dropped lo * lo term is
 // 2^-18 relative), all accumulated in the same fp32 TMEM tile: three K loops per tap instead of one.
-template <int BLOCK_N, int MODE, int KIND, int UPS = 0, int TAP3 = 0, int SPLIT = 0>
+// ACT 1: exact (erf) GELU instead of the ReLU flag (fc1 of the ViT MLP, csrc/vit.cu), its own instantiation.
+template <int BLOCK_N, int MODE, int KIND, int UPS = 0, int TAP3 = 0, int SPLIT = 0, int ACT = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -446,7 +447,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   float a0 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e]) + bb[2 * e];
                   float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
                   if constexpr (UPS) { a0 += __uint_as_float(uw[e] << 16); a1 += __uint_as_float(uw[e] & 0xffff0000u); }
-                  if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                  if constexpr (ACT == 1) {
+                    a0 = 0.5f * a0 * (1.0f + erff(a0 * 0.70710678118654752f));
+                    a1 = 0.5f * a1 * (1.0f + erff(a1 * 0.70710678118654752f));
+                  } else if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
                   if (zero_row) { a0 = 0.f; a1 = 0.f; }
                   if constexpr (SPLIT) {
                     const __nv_bfloat162 hi2 = __floats2bfloat162_rn(a0, a1);
@@ -739,12 +743,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 }
 
 
-template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0, int TAP3 = 0, int SPLIT = 0>
+template <int BLOCK_N, int MODE, int KIND = 0, int UPS = 0, int TAP3 = 0, int SPLIT = 0, int ACT = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
                        cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    LVC_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const int smem = gemm_smem_bytes(BLOCK_N, MODE, p.num_stages, p.phase_cols, p.has_res) +
@@ -763,9 +767,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT>, ta, tw, td, tr, p));
+    LVC_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT, ACT>, ta, tw, td, tr, p));
   } else {
-    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
+    gemm_bf16_tc_kernel<BLOCK_N, MODE, KIND, UPS, TAP3, SPLIT, ACT><<<grid, kGemmThreads, smem, s>>>(ta, tw, td, tr, p);
   }
   return check_launch("gemm_bf16_tc_kernel");
 }
@@ -816,6 +820,7 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
   LVC_REQUIRE(d->N % 8 == 0, "gemm: N must be a multiple of 8");
   const bool tf32 = d->a_dtype == LVCB200_F32;   // fp32 operands consumed by the tensor core as TF32
   const bool split = d->split_rows != 0;         // strict mode: hi/lo bf16 pair operands, three-term product
+  LVC_REQUIRE(d->relu >= 0 && d->relu <= 2 && !(d->relu == 2 && split), "gemm: relu must be 0, 1 (ReLU) or 2 (erf GELU; not with split operands)");
   LVC_REQUIRE(!split || (!tf32 && d->split_rows >= d->M && d->split_rows % BLOCK_M == 0 && d->split_rows < (1ll << 30) &&
                          !d->upsample_add && d->d_dtype != LVCB200_F16 && d->K % BLOCK_K == 0),
               "gemm: split mode: bf16 pairs, split_rows a multiple of 128 and >= M, K % 64 == 0, no upsample_add, bf16 (pair) or fp32 output");
@@ -912,7 +917,7 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
     const int two_cta = e_2 ? atoi(e_2) : 2;   // default: 2-CTA tiles for the big 3x3 convs only (same-box A/B: dense stack -1.7 % sustained)
     // 1: every eligible layer; 2 (default): long K loops on wide tiles -- the big 3x3 convs and the fc layers (per-shape table in
     // profiles/r01_gemm_modes.md: the pair handshake is amortised and half the B bytes per SM buy two more ring stages); 3: big 3x3 only
-    const bool want2 = p.up ? false : two_cta == 1 || (two_cta == 3 && d->taps == 9 && bn == 256 && d->M >= 100000) ||
+    const bool want2 = (p.up || d->relu == 2) ? false : two_cta == 1 || (two_cta == 3 && d->taps == 9 && bn == 256 && d->M >= 100000) ||
                        (two_cta == 2 && bn == 256 && !p.has_res && k_iters >= 16 && (d->M >= 100000 || (d->taps == 1 && d->M >= 8000)));
     if (want2 && mode == 1 && !tf32 && bn >= 64 && d->M >= 256) {
       GemmParams p2 = p;
@@ -932,6 +937,10 @@ extern "C" int lvcb200_gemm_bf16(const lvcb200_gemm_desc* d, void* stream) {
     }
   }
   if (p.up) return launch_gemm<256, 1, 0, 1>(ta, tw, td, tr, p, s);
+  if (d->relu == 2) {   // GELU epilogue: its own instantiation (wide bf16 layers without residual: the ViT's fc1)
+    LVC_REQUIRE(mode == 1 && bn == 256 && !tf32 && !p.has_res && !p.warp_epi, "gemm: relu = 2 (GELU) needs a bf16 output with N >= 129 and no residual");
+    return launch_gemm<256, 1, 0, 0, 0, 0, 1>(ta, tw, td, tr, p, s);
+  }
   {  // 3x3 conv on a 64-wide tile (res2 conv2): the three kw taps share one A tile (TAP3 instantiation)
     static const char* e_t3 = getenv("LVCB200_GEMM_TAP3");
     bool tap3 = (e_t3 == nullptr || atoi(e_t3) != 0) && d->taps == 9 && bn == 64 && mode == 1 && !tf32 && !p.has_res && !p.warp_epi &&

@@ -74,6 +74,14 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
 all_gather_bank.last_check = None
 
 
+def get_descriptors(model, image, boxes, mean, std, operation="context", size=224):
+    """The per-image body of get_descriptors (tools/run_nearest_neighbours.py:108-128) without leaving the device: context crops of the
+    boxes (lvc/data/utils.py:485-519 via lvcb200_crops_qe, normalised like preprocess_crops :102-105) -> ``model(crops)`` (the DINO ViT,
+    lvc_b200.modeling.DinoViT) -> crop_feats [n, dim] fp32 on the device, ready for assemble_tensors / KnnBank."""
+    from .crops import get_crops_qe
+    return model(get_crops_qe(image, boxes, operation, size, mean, std))
+
+
 def run_nearest_neighbours(shot_classes, shot_descriptors, query_features: List[dict], cosine: bool = True,
                            device: Optional[torch.device] = None, topk: int = 10):
     """tools/run_nearest_neighbours.py:142-162.  Sets ``top10_shots`` ([Qi, 10] int64 class votes, best first) on every

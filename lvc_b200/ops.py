@@ -51,7 +51,7 @@ def _desc_key(d):
 
 
 def chain_eligible(d):
-    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0 and not d.upsample_add and not d.split_rows
+    return d.a_dtype == BF16 and d.d_dtype == BF16 and d.N % 64 == 0 and d.K % 64 == 0 and not d.upsample_add and not d.split_rows and d.relu != 2
 
 
 def run_chain(rec, record=True):
@@ -477,7 +477,7 @@ def gemm(A, W, bias=None, residual=None, out=None, out_dtype=torch.bfloat16, rel
     d.M, d.N, d.K, d.taps = M, N, K, taps
     for i, s in enumerate(shifts):
         d.shift[i] = int(s)
-    d.relu = int(relu)
+    d.relu = 2 if relu == "gelu" else int(relu)
     d.split_rows = int(split_rows)
     d.plane_h, d.plane_w = plane_hw if plane_hw else (0, 0)
     if upsample_add is not None:

@@ -271,3 +271,16 @@ def test_pair_elementwise_kernels():
     rois, rimg = ops.make_rois(props, counts)
     assert torch.equal(rois[:, 1:], props.view(-1, 4)) and torch.equal(rois[:, 0], torch.arange(3, device=DEV).repeat_interleave(50).float())
     assert torch.equal(rimg.view(3, 50)[2], torch.where(torch.arange(50, device=DEV) < 17, 2, -1).int()) and int(rimg.view(3, 50)[1].max()) == -1
+
+
+def test_gemm_gelu_epilogue():
+    """relu="gelu": exact (erf) GELU fused into the staged epilogue (fc1 of the ViT MLP) against torch's nn.GELU on the fp32 product."""
+    g = torch.Generator(device="cpu").manual_seed(12)
+    M, N, K = 1570, 1536, 384
+    a = torch.randn(M, K, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5 * 2).bfloat16().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = ops.gemm(a, w, bias=bias, relu="gelu")
+    _close(out, F.gelu(_ref_mm(a, w) + bias), True)
+    with pytest.raises(Exception):
+        ops.gemm(a, w[:64], bias=bias[:64], relu="gelu")           # narrow layers have no GELU instantiation
