@@ -15,7 +15,7 @@ from lvc_b200 import ops  # noqa: E402
 from lvc_b200.modeling import DetectorEngine  # noqa: E402
 from lvc_b200.weights import synthetic_state_dict  # noqa: E402
 
-TF, GBS, _ = bench.measured_peaks()
+TF, GBS, _, _ = bench.measured_peaks()
 
 cfg = bench.bench_cfg()
 eng = DetectorEngine(cfg, synthetic_state_dict(cfg, 0))
