@@ -341,6 +341,17 @@ int lvcb200_match_boxes(const float* gt_boxes, int64_t G, const float* boxes, co
                         int allow_low_quality_matches, int64_t* matches, int8_t* match_labels, float* matched_vals, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* subsample_labels (detectron2/modeling/sampling.py:9-54) for n_vectors label vectors [n_vectors, N] (int64, or int8 when
+ * labels_are_int8) with the two torch.randperm draws replaced by caller-supplied random keys [n_vectors, N] uint32: the positives
+ * (label != -1 && != bg_label) / negatives (== bg_label) with the smallest (key, index) pairs are taken, in that order
+ * (== cls_idx[argsort(keys[cls_idx], stable)[:take]]); num_pos = min(n_pos, int(num_samples * positive_fraction)),
+ * num_neg = min(n_neg, num_samples - num_pos).  pos_idx / neg_idx: [n_vectors, num_samples] int64, -1 beyond counts[v] = {num_pos,
+ * num_neg} (int32 [n_vectors, 2]).  out_labels (optional, int8 [n_vectors, N]): RPN._subsample_labels (rpn.py:249-266): -1 everywhere,
+ * 1 at the sampled positives, 0 at the sampled negatives.  No host synchronisation; num_samples <= 1024. */
+int lvcb200_subsample_labels(const void* labels, int labels_are_int8, const uint32_t* keys, int n_vectors, int64_t N, int num_samples,
+                             double positive_fraction, int64_t bg_label, int64_t* pos_idx, int64_t* neg_idx, int32_t* counts,
+                             int8_t* out_labels, void* stream);
+
 /* RPN.losses (detectron2/modeling/proposal_generator/rpn.py:328-400) before normalisation and loss weights: out2[0] = sum of
  * binary_cross_entropy_with_logits over anchors with gt_labels >= 0, out2[1] = sum of smooth_l1(pred_anchor_deltas -
  * Box2BoxTransform(weights).get_deltas(anchors, gt_boxes), beta) over gt_labels == 1 (beta < 1e-5: L1).  anchors [A,4] (all levels

@@ -6,6 +6,7 @@ C / numpy oracle and -- on the GPU box -- the CUDA path against them.  Kept smal
 """
 import os
 import sys
+import types
 
 import numpy as np
 import torch
@@ -436,10 +437,56 @@ def gold_training_ops():
     save("training_ops", **out)
 
 
+def gold_sampling():
+    """"Next" row f4: subsample_labels (detectron2/modeling/sampling.py:9-54) and RPN._subsample_labels (rpn.py:249-266), executed from
+    the reference with ``torch.randperm(n)`` standing on per-element random keys: the i-th call returns the stable argsort of the keys
+    of the class it permutes (first the positives, then the negatives -- the order sampling.py:49-50 draws them in)."""
+    import detectron2.modeling.sampling as S
+    from detectron2.modeling.proposal_generator.rpn import RPN
+    rng = np.random.default_rng(77)
+    out = {}
+    real = torch.randperm
+    cases = {"rpn": (20000, 256, 0.5, 0, [0.93, 0.06, 0.01]), "roi": (2100, 512, 0.25, 80, None), "few": (300, 256, 0.5, 0, [0.2, 0.75, 0.05]),
+             "ties": (4000, 64, 0.5, 0, [0.5, 0.3, 0.2])}
+    for tag, (n, ns, frac, bg, p) in cases.items():
+        if tag == "roi":
+            labels = rng.integers(0, 80, n).astype(np.int64)
+            labels[rng.random(n) < 0.85] = 80
+            labels[rng.random(n) < 0.02] = -1
+        else:
+            labels = rng.choice(np.array([-1, 0, 1], np.int64), size=n, p=p)
+        keys = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+        if tag == "ties":
+            keys = (keys % 7).astype(np.uint32)                 # many equal keys: the stable order decides
+        lt, kt = torch.from_numpy(labels), torch.from_numpy(keys.astype(np.int64))
+        subsets = [torch.nonzero((lt != -1) & (lt != bg)).flatten(), torch.nonzero(lt == bg).flatten()]
+        calls = []
+
+        def fake(m, device=None, _s=subsets, _c=calls):
+            sub = _s[len(_c)]
+            assert m == sub.numel()
+            _c.append(m)
+            return torch.argsort(kt[sub], stable=True)
+        torch.randperm = fake
+        try:
+            pos, neg = S.subsample_labels(lt, ns, frac, bg)
+            if tag in ("rpn", "few"):
+                del calls[:]
+                me = types.SimpleNamespace(batch_size_per_image=ns, positive_fraction=frac)
+                out[f"{tag}_rpn_label"] = RPN._subsample_labels(me, lt.to(torch.int8).clone()).numpy()
+        finally:
+            torch.randperm = real
+        out.update({f"{tag}_labels": labels, f"{tag}_keys": keys, f"{tag}_args": np.array([ns, frac, bg], np.float64),
+                    f"{tag}_pos": pos.numpy(), f"{tag}_neg": neg.numpy()})
+    save("sampling", **out)
+
+
 def main():
     which = sys.argv[1:] or ["nms", "pooler", "rpn", "frcnn", "knn", "e2e", "corrector", "cand", "crops", "train"]
     if "train" in which:
         gold_training_ops()
+    if "sampling" in which:
+        gold_sampling()
     if "cand" in which:
         gold_candidates()
     if "crops" in which:

@@ -466,3 +466,18 @@ def fast_rcnn_losses(logits, deltas, gt_classes, proposals, gt_boxes, weights=(1
     lib().orc_fast_rcnn_losses(_p(lg, _f32p), _p(dl, _f32p), dl.shape[1], _p(gc, _i64p), _p(pr, _f32p), _p(gb, _f32p), ctypes.c_int64(R), K1 - 1,
                                _p(_f32(weights), _f32p), ctypes.c_float(beta), _p(out, _f64p))
     return out
+
+
+def subsample_labels(labels, keys, num_samples, positive_fraction, bg_label):
+    """detectron2/modeling/sampling.py:9-54 with the two ``torch.randperm`` draws replaced by the stable argsort of per-element
+    random keys (``keys`` uint32 [N]): positive[argsort(keys[positive])[:num_pos]], negative[argsort(keys[negative])[:num_neg]].
+    Returns (pos_idx, neg_idx) int64."""
+    labels = np.asarray(labels).astype(np.int64)
+    keys = np.asarray(keys, np.uint32)
+    positive = [i for i in range(len(labels)) if labels[i] != -1 and labels[i] != bg_label]
+    negative = [i for i in range(len(labels)) if labels[i] == bg_label]
+    num_pos = min(len(positive), int(num_samples * positive_fraction))
+    num_neg = min(len(negative), num_samples - num_pos)
+    pos = sorted(positive, key=lambda i: (int(keys[i]), i))[:num_pos]
+    neg = sorted(negative, key=lambda i: (int(keys[i]), i))[:num_neg]
+    return np.asarray(pos, np.int64), np.asarray(neg, np.int64)

@@ -496,3 +496,45 @@ def test_model_candidate_flags_through_public_api():
     assert res["num_candidates"] == int((want == 1).sum()) and len(res["annotations"]) == int((want != 0).sum())
     ids = [a["id"] for a in res["annotations"]]
     assert ids == sorted(ids) and ids == (want != 0).nonzero().flatten().add(1).tolist()   # loadRes' running index over all detections
+
+
+# ---------------------------------------------------------------------------------------------- f4: subsample_labels
+def test_subsample_labels_vs_reference_and_oracle(golden):
+    """lvcb200_subsample_labels against the reference's subsample_labels / RPN._subsample_labels outputs (tests/golden/sampling.npz:
+    randperm standing on the fixture's keys) -- index vectors identical, in order -- and against the oracle on a batch of full-size RPN
+    label vectors (268 569 anchors) incl. heavy key ties; counts follow min(n_pos, int(ns * frac)), min(n_neg, ns - n_pos)."""
+    from lvc_b200.modeling import subsample_labels, subsample_labels_batched, subsample_rpn_labels
+    g = golden("sampling")
+    for tag in ("rpn", "roi", "few", "ties"):
+        ns, frac, bg = g[f"{tag}_args"]
+        lab = torch.from_numpy(g[f"{tag}_labels"]).to(DEV)
+        keys = torch.from_numpy(g[f"{tag}_keys"].astype(np.int64)).to(DEV)
+        pos, neg = subsample_labels(lab, int(ns), float(frac), int(bg), keys=keys)
+        assert np.array_equal(pos.cpu().numpy(), g[f"{tag}_pos"]) and np.array_equal(neg.cpu().numpy(), g[f"{tag}_neg"]), tag
+        if f"{tag}_rpn_label" in g.files:
+            out = subsample_rpn_labels(lab.to(torch.int8), int(ns), float(frac), keys=keys)
+            assert np.array_equal(out.cpu().numpy(), g[f"{tag}_rpn_label"]), tag
+    rng = np.random.default_rng(9)
+    V, A = 3, 268569
+    lab = rng.choice(np.array([-1, 0, 1], np.int8), size=(V, A), p=[0.3, 0.699, 0.001])
+    keys = rng.integers(0, 2 ** 32, (V, A), dtype=np.uint64).astype(np.uint32)
+    keys[1] = keys[1] % 50                                  # thousands of elements share the threshold key
+    keys[2] = 12345                                         # all keys equal: pure index order
+    pos, neg, counts = subsample_labels_batched(torch.from_numpy(lab).to(DEV), 256, 0.5, 0, keys=torch.from_numpy(keys.astype(np.int64)).to(DEV))
+    for v in range(V):
+        wp, wn = O.subsample_labels(lab[v], keys[v], 256, 0.5, 0)
+        c = counts[v].tolist()
+        assert c == [len(wp), len(wn)] and sum(c) == 256
+        assert np.array_equal(pos[v, :c[0]].cpu().numpy(), wp) and np.array_equal(neg[v, :c[1]].cpu().numpy(), wn), v
+        assert bool((pos[v, c[0]:] == -1).all()) and bool((neg[v, c[1]:] == -1).all())
+    # keys drawn from torch's generator: a valid sample (right counts, right classes, no duplicates), different from call to call
+    l1 = torch.from_numpy(lab[0].astype(np.int64)).to(DEV)
+    a = subsample_labels(l1, 512, 0.25, 0)
+    b = subsample_labels(l1, 512, 0.25, 0)
+    assert len(a[0]) == 128 and len(a[1]) == 384 and bool((l1[a[0]] == 1).all()) and bool((l1[a[1]] == 0).all())
+    assert len(torch.unique(torch.cat(a))) == 512 and not torch.equal(a[1], b[1])
+    # empty vector, and no positives / no negatives at all
+    e = subsample_labels(torch.zeros(0, dtype=torch.int64, device=DEV), 256, 0.5, 0)
+    assert len(e[0]) == 0 and len(e[1]) == 0
+    p_only = subsample_labels(torch.ones(100, dtype=torch.int64, device=DEV), 64, 0.5, 0)
+    assert len(p_only[0]) == 32 and len(p_only[1]) == 0
