@@ -363,6 +363,17 @@ def pipeline_section(model, sd, dev, per_image=2.0):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         out[tag] = {"ms_per_call": ms, "images_per_s": BATCH / (ms / 1e3), **miner.stats}
+        # the same calls software-pipelined (miner.stream: three batches in flight); wall clock around the whole run, device idle on both sides
+        n_b = 12
+        for _ in miner.stream(inputs for _ in range(4)):
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in miner.stream(inputs for _ in range(n_b)):
+            pass
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[tag].update(stream_ms_per_batch=dt / n_b * 1e3, stream_images_per_s=BATCH * n_b / dt)
     return out
 
 

@@ -83,6 +83,7 @@ class PseudoLabelMiner:
         self.inv_std = 1.0 / torch.as_tensor(pixel_std, dtype=torch.float32, device=dev)
         self.swap, self.operation, self.size, self.max_batch = bool(swap_channels), operation, int(crop_size), int(max_descriptor_batch)
         self.stats = {}
+        self._host_ring, self._img_ring = {}, {}
 
     # --------------------------------------------------------------------------------------------------------------- stages
     def _crops(self, image: torch.Tensor, windows: np.ndarray) -> torch.Tensor:
@@ -101,11 +102,14 @@ class PseudoLabelMiner:
             return self.descriptor(crops)
         return torch.cat([self.descriptor(crops[i:i + self.max_batch]) for i in range(0, crops.shape[0], self.max_batch)])
 
-    @torch.no_grad()
-    def __call__(self, batched_inputs: List[dict]) -> List[dict]:
+    # ------------------------------------------------------------------------------------------------------------- pipeline
+    # label(): everything up to the packed D2H of the detections is enqueued without waiting; verify(): needs the host copy (the number
+    # of candidates sizes the ViT batch), enqueues crops -> ViT -> kNN (-> corrector) and their D2H; finish(): assembles the result.
+    def _label(self, batched_inputs: List[dict], images=None):
         det = self.detector
         dev = det._device
-        images = det.to_device(batched_inputs)
+        if images is None:
+            images = det.to_device(batched_inputs)
         sizes = [tuple(im.shape[-2:]) for im in images]
         outs = [(int(x.get("height", s[0])), int(x.get("width", s[1]))) for x, s in zip(batched_inputs, sizes)]
         boxes, scores, classes, rows, counts = det.engine.run(images, outs)
@@ -113,8 +117,19 @@ class PseudoLabelMiner:
         flags, _ = self.filter(boxes, scores, classes, counts, outs, ids if all(i is not None for i in ids) else None)
         n, k = scores.shape
         # the one host round trip in front of the verifier: detections + flags, packed
-        host = torch.cat([boxes.reshape(n, 4 * k), scores, classes.float(), flags.float(), counts.float()[:, None]], dim=1).cpu()
+        packed = torch.cat([boxes.reshape(n, 4 * k), scores, classes.float(), flags.float(), counts.float()[:, None]], dim=1)
+        key = tuple(packed.shape)
+        ring = self._host_ring.setdefault(key, [[torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True) for _ in range(4)], 0])
+        host = ring[0][ring[1] % 4]
+        ring[1] += 1
+        host.copy_(packed, non_blocking=True)
+        return dict(images=images, sizes=sizes, outs=outs, host=host, k=k, ready=torch.cuda.current_stream(dev).record_event())
 
+    def _verify(self, st):
+        dev = self.detector._device
+        st["ready"].synchronize()
+        host, k, images, sizes, outs = st["host"], st["k"], st["images"], st["sizes"], st["outs"]
+        n = len(outs)
         results, cand = [], []          # cand: per image (indices into the detections, fp32 boxes in the input frame, windows)
         for i, o in enumerate(outs):
             c = int(host[i, -1])
@@ -128,61 +143,117 @@ class PseudoLabelMiner:
             sel, fb, win = sel[torch.from_numpy(ok)], fb[ok], win[ok]
             cand.append((sel, fb, win))
             results.append({"instances": inst})
-
         m = [len(c[0]) for c in cand]
         total = sum(m)
-        self.stats = {"detections": int(host[:, -1].sum()), "candidates": total}
+        st.update(results=results, cand=cand, m=m, total=total, detections=int(host[:, -1].sum()), out=None)
         if total:
             crops = torch.cat([self._crops(images[i], cand[i][2]) for i in range(n) if m[i]])
             feats = self._describe(crops)
-            qcls = torch.cat([results[i]["instances"].pred_classes[cand[i][0]] for i in range(n)]).to(dev)
+            qcls = torch.cat([results[i]["instances"].pred_classes[cand[i][0]] for i in range(n)]).to(dev, non_blocking=True)
             res = self.bank.verify(feats, qcls, topk=10, knn=self.knn)
-            keep, votes = res["keep"].to(torch.int64).cpu(), res["votes"].cpu()
-            feats_h = feats.cpu()
+            D = feats.shape[1]
+            out = torch.cat([feats, res["votes"].float(), res["keep"].float()[:, None]], dim=1)       # [total, D + 10 + 1], one D2H
+            if self.corrector is not None:
+                # train_net_reg_qe.py --eval-only (GeneralizedRCNNRegOnly.inference, rcnn.py:372-410) on the same device images.  The
+                # heads run on every candidate (their count is known here without another round trip); only the verified rows are used.
+                pyramid, _ = self.corrector.engine.run_features(images)
+                planes = [pyramid[l] for l in (2, 3, 4, 5)]
+                reg = self.corrector.head(planes, [torch.from_numpy(c[1]).reshape(-1, 4).to(dev, non_blocking=True) for c in cand], sizes)
+                out = torch.cat([out, torch.cat(reg)], dim=1)
+            hout = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+            hout.copy_(out, non_blocking=True)
+            st.update(out=hout, D=D)
+        st["done"] = torch.cuda.current_stream(dev).record_event()
+        return st
+
+    def _finish(self, st) -> List[dict]:
+        st["done"].synchronize()
+        results, cand, m, total, sizes, outs = st["results"], st["cand"], st["m"], st["total"], st["sizes"], st["outs"]
+        hout = st["out"]
+        D = st.get("D", getattr(self.bank, "D", 0))
         off = 0
-        kept_boxes = []
+        verified = 0
         for i, (sel, fb, win) in enumerate(cand):
-            inst = results[i]["instances"]
+            inst, o = results[i]["instances"], outs[i]
             ci = Instances(sizes[i])
             ci.gt_boxes = Boxes(torch.from_numpy(fb).reshape(-1, 4))
             ci.gt_classes = inst.pred_classes[sel]
             ci.scores = inst.scores[sel]
             ci.det_index = sel
-            if total:
-                ci.crop_feats = feats_h[off:off + m[i]]
-                ci.top10_shots = votes[off:off + m[i]]
-                ci.keep = keep[off:off + m[i]]
-            else:
-                ci.crop_feats = torch.zeros((0, getattr(self.bank, "D", 0)))
-                ci.top10_shots = torch.zeros((0, 10), dtype=torch.int64)
-                ci.keep = torch.zeros(0, dtype=torch.int64)
+            rows = hout[off:off + m[i]] if total else torch.zeros((0, D + 15))
+            ci.crop_feats = rows[:, :D].clone()
+            ci.top10_shots = rows[:, D:D + 10].to(torch.int64)
+            ci.keep = rows[:, D + 10].to(torch.int64)
             off += m[i]
             results[i]["candidates"] = ci
-            kept_boxes.append(ci.gt_boxes.tensor[ci.keep.bool()])
-        self.stats["verified"] = int(sum(len(b) for b in kept_boxes))
-
-        corrected: List[Optional[torch.Tensor]] = [None] * n
-        if self.corrector is not None and self.stats["verified"]:
-            # train_net_reg_qe.py --eval-only on the verified boxes (GeneralizedRCNNRegOnly.inference, rcnn.py:372-410), same device images
-            pyramid, _ = self.corrector.engine.run_features(images)
-            planes = [pyramid[l] for l in (2, 3, 4, 5)]
-            reg = self.corrector.head(planes, [b.to(dev) for b in kept_boxes], sizes)
-            corrected = [r.cpu() for r in reg]
-        for i, o in enumerate(outs):
-            inst, ci = results[i]["instances"], results[i]["candidates"]
             kb = ci.keep.bool()
+            verified += int(kb.sum())
             pl = Instances(o)
-            if corrected[i] is not None:
-                sx, sy = o[1] / sizes[i][1], o[0] / sizes[i][0]                 # detector_postprocess, postprocessing.py:37-59
-                b = corrected[i].clone()
-                b[:, 0::2] *= sx
-                b[:, 1::2] *= sy
+            if self.corrector is not None and total:
+                b = rows[:, D + 11:D + 15][kb].clone()
+                b[:, 0::2] *= o[1] / sizes[i][1]                              # detector_postprocess, postprocessing.py:37-59
+                b[:, 1::2] *= o[0] / sizes[i][0]
                 bx = Boxes(b)
                 bx.clip(o)
                 pl.pred_boxes = bx
             else:
-                pl.pred_boxes = Boxes(inst.pred_boxes.tensor[ci.det_index[kb]].clone())
+                pl.pred_boxes = Boxes(inst.pred_boxes.tensor[sel[kb]].clone())
             pl.pred_classes = ci.gt_classes[kb]
             pl.scores = ci.scores[kb]
             results[i]["pseudo_labels"] = pl
+        self.stats = {"detections": st["detections"], "candidates": total, "verified": verified}
         return results
+
+    @torch.no_grad()
+    def __call__(self, batched_inputs: List[dict]) -> List[dict]:
+        return self._finish(self._verify(self._label(batched_inputs)))
+
+    @torch.no_grad()
+    def stream(self, batches):
+        """``miner(inputs)`` for every batch of the iterable, in order, software-pipelined: while the GPU runs the detector on batch i
+        the host selects the candidates of batch i - 1 and enqueues their crops / ViT / kNN behind it, and assembles the result of
+        batch i - 2 -- no stage waits for the device with nothing queued behind it.  The H2D copy of the next batch runs on a copy
+        stream, into persistent device image sets (three batches are in flight: five sets per shape)."""
+        from collections import deque
+        dev = self.detector._device
+        main, copy_stream = torch.cuda.current_stream(dev), torch.cuda.Stream(device=dev)
+
+        def stage(batched_inputs):
+            key = tuple((tuple(x["image"].shape), x["image"].dtype) for x in batched_inputs)
+            ring = self._img_ring.get(key)
+            if ring is None:
+                while len(self._img_ring) >= 3:
+                    self._img_ring.pop(next(iter(self._img_ring)))
+                ring = self._img_ring[key] = {"sets": [[torch.empty(sh, dtype=dt, device=dev) for sh, dt in key] for _ in range(5)],
+                                              "free": [None] * 5, "n": 0}
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_stream(main)               # new blocks may recycle memory a queued kernel still reads
+            slot = ring["n"] % 5
+            ring["n"] += 1
+            images = ring["sets"][slot]
+            with torch.cuda.stream(copy_stream):
+                if ring["free"][slot] is not None:
+                    copy_stream.wait_event(ring["free"][slot])  # the set's previous user (five batches ago) has been verified
+                for dst, x in zip(images, batched_inputs):
+                    dst.copy_(x["image"], non_blocking=True)
+                ready = copy_stream.record_event()
+            return batched_inputs, images, ready, (ring, slot)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None
+        labelled, verified = deque(), deque()
+        while staged is not None or labelled or verified:
+            if staged is not None:
+                batched_inputs, images, ready, ring = staged
+                nxt = next(it, None)
+                staged_next = stage(nxt) if nxt is not None else None
+                main.wait_event(ready)
+                labelled.append((self._label(batched_inputs, images), ring))
+                staged = staged_next
+            if labelled and (len(labelled) > 1 or staged is None):
+                st, ring = labelled.popleft()
+                verified.append(self._verify(st))
+                ring[0]["free"][ring[1]] = st["done"]
+            if verified and (len(verified) > 1 or (staged is None and not labelled)):
+                yield self._finish(verified.popleft())

@@ -126,3 +126,32 @@ def test_miner_no_candidates():
     miner = PseudoLabelMiner(det, vit, bank, CandidateFilter([1, 2], 0.999, 1.0))
     out = miner([{"image": torch.zeros(3, 128, 160, dtype=torch.uint8)}])
     assert miner.stats["candidates"] == 0 and len(out[0]["pseudo_labels"]) == 0 and len(out[0]["candidates"]) == 0
+
+
+def test_miner_stream_equals_blocking_calls():
+    """miner.stream(batches) (three batches in flight, copy stream, deferred assembly) returns what miner(batch) returns, in order."""
+    cfg = DetectorConfig(depth=50, score_thresh_test=0.0)
+    sd = synthetic_state_dict(cfg, 0)
+    det = GeneralizedRCNN(cfg, sd, use_cuda_graph=True)
+    vit = DinoViT(synthetic_vit_state_dict(depth=2, seed=2))
+    g = torch.Generator().manual_seed(5)
+    bank = ops.KnnBank(torch.randn(80, 384, generator=g).cuda(), torch.randint(0, 4, (80,), generator=g).cuda())
+    ccfg = DetectorConfig(depth=50, num_fc=3)
+    full = {k: v for k, v in sd.items() if not k.startswith("roi_heads.")}
+    full.update(synthetic_corrector_head(ccfg, 3))
+    miner = PseudoLabelMiner(det, vit, bank, CandidateFilter(range(0, 80, 3), 0.03, 1.0), corrector=GeneralizedRCNNRegOnly(ccfg, full))
+    shapes = [(192, 256)] * 3 + [(160, 224)] * 2 + [(192, 256)] * 4
+    batches = [[{"image": (torch.rand(3, h, w, generator=g) * 255).to(torch.uint8), "height": h, "width": w, "image_id": 2 * b + j} for j in range(2)]
+               for b, (h, w) in enumerate(shapes)]
+    want = [miner(b) for b in batches]
+    n_cand = 0
+    got = list(miner.stream(iter(batches)))
+    assert len(got) == len(want)
+    for rb, wb in zip(got, want):
+        for r, w in zip(rb, wb):
+            assert torch.equal(r["instances"].pred_boxes.tensor, w["instances"].pred_boxes.tensor)
+            assert torch.equal(r["candidates"].keep, w["candidates"].keep) and torch.equal(r["candidates"].top10_shots, w["candidates"].top10_shots)
+            assert torch.equal(r["pseudo_labels"].pred_boxes.tensor, w["pseudo_labels"].pred_boxes.tensor)
+            n_cand += len(r["candidates"])
+    assert n_cand > 0
+    assert list(miner.stream([])) == []

@@ -1,7 +1,7 @@
 #!/bin/bash
 # miner tests + the pipeline bench section alone
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_mining.py -x -q 2>&1 | tail -15
+python -m pytest tests/test_gpu_mining.py -x -q 2>&1 | tail -25
 python - <<'PY' 2>&1 | tail -20
 import json, torch, bench
 from lvc_b200.modeling import GeneralizedRCNN
