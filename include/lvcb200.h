@@ -321,6 +321,10 @@ int lvcb200_layernorm(const void* x, int64_t rows, int D, int64_t ldx, const flo
                       int out_dtype, int64_t ldo, void* stream);
 int lvcb200_gelu(void* x, int64_t n, void* stream);
 int lvcb200_attention(const void* qkv, int B, int N, int H, int head_dim, float scale, void* out, void* stream);
+/* The same attention on tcgen05.mma / TMEM (attention_tc.cu): S = Q K^T and O = P V on the 5th-generation tensor cores (Q, K, V tiles by
+ * TMA straight out of qkv; V consumed as an MN-major operand), softmax by two threads per query row straight out of TMEM.  qkv / out as
+ * for lvcb200_attention; out must be 16-byte aligned. */
+int lvcb200_attention_tc(const void* qkv, int B, int N, int H, int head_dim, float scale, void* out, void* stream);
 
 /* "Next" row: training-side users of the path's operators.
  * roi_align_backward: autograd backward of detectron2.layers.roi_align (ROIAlign_cuda.cu:141-306 RoIAlignBackwardFeature):

@@ -115,6 +115,7 @@ _SIGS = {
     "lvcb200_layernorm": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int64, c_void_p]),
     "lvcb200_gelu": (c_int, [c_void_p, c_int64, c_void_p]),
     "lvcb200_attention": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "lvcb200_attention_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "lvcb200_candidate_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                          ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "lvcb200_make_rois": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "liblvcb200.so")
-SOURCES = ["capi.cu", "roi_align.cu", "nms.cu", "rpn.cu", "detections.cu", "knn.cu", "knn_tc3.cu", "gemm_tc.cu", "gemm_chain.cu", "misc.cu", "train_ops.cu", "candidates.cu", "sampling.cu", "vit.cu"]
+SOURCES = ["capi.cu", "roi_align.cu", "nms.cu", "rpn.cu", "detections.cu", "knn.cu", "knn_tc3.cu", "gemm_tc.cu", "gemm_chain.cu", "misc.cu", "train_ops.cu", "candidates.cu", "sampling.cu", "vit.cu", "attention_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

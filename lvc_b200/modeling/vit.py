@@ -39,7 +39,7 @@ def synthetic_vit_state_dict(dim=384, depth=12, heads=6, patch=8, img=224, mlp_r
 class DinoViT:
     """``model(crops [B,3,S,S] fp32 CUDA, normalised) -> [B, dim] fp32`` like the hub model's forward (inference only)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", heads=6, patch=8, eps=1e-6):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", heads=6, patch=8, eps=1e-6, attention="tc"):
         _lib.load()
         self.device = torch.device(device)
         sd = {k: v.detach().float() for k, v in state_dict.items()}
@@ -61,6 +61,9 @@ class DinoViT:
                                     fc1=(w(p + "mlp.fc1.weight"), f(p + "mlp.fc1.bias")), fc2=(w(p + "mlp.fc2.weight"), f(p + "mlp.fc2.bias"))))
         self.norm = (f("norm.weight"), f("norm.bias"))
         self.debug = None
+        if attention not in ("tc", "mma"):
+            raise ValueError("DinoViT: attention must be 'tc' (tcgen05 / TMEM kernel) or 'mma' (mma.sync kernel)")
+        self.attention = attention
 
     def eval(self):
         return self
@@ -97,7 +100,10 @@ class DinoViT:
             h = self._ln(x, blk["n1"])
             qkv = ops.gemm(h, blk["qkv"][0], bias=blk["qkv"][1])
             a = torch.empty((B * N, D), dtype=bf, device=dev)
-            _lib.check(lib.lvcb200_attention(_lib.ptr(qkv), B, N, H, D // H, scale, _lib.ptr(a), _lib.stream_ptr()), "lvcb200_attention")
+            if self.attention == "tc":
+                _lib.check(lib.lvcb200_attention_tc(_lib.ptr(qkv), B, N, H, D // H, scale, _lib.ptr(a), _lib.stream_ptr()), "lvcb200_attention_tc")
+            else:
+                _lib.check(lib.lvcb200_attention(_lib.ptr(qkv), B, N, H, D // H, scale, _lib.ptr(a), _lib.stream_ptr()), "lvcb200_attention")
             x = ops.gemm(a, blk["proj"][0], bias=blk["proj"][1], residual=x)     # x + proj(attn(norm1(x)))
             h = self._ln(x, blk["n2"])
             m = ops.gemm(h, blk["fc1"][0], bias=blk["fc1"][1], relu="gelu")         # erf GELU in the GEMM's epilogue
