@@ -27,6 +27,20 @@ constexpr int FA_THREADS = 320;                    // TMA warp, MMA warp, eight 
 constexpr int FA_SMEM = (1 + FA_RING + 2) * FA_TILE + 1024 + 256 + 2048;
 constexpr int FA_TMEM_COLS = 256;
 
+#ifdef LVCB200_FA_TRACE
+__device__ unsigned long long g_fa_trace[256];
+#define FA_STAMP(slot)                                                                        \
+  do {                                                                                        \
+    if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) {                              \
+      unsigned long long t_;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                  \
+      g_fa_trace[slot] = t_;                                                                  \
+    }                                                                                         \
+  } while (0)
+#else
+#define FA_STAMP(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ uint32_t fa_pack(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -38,18 +52,21 @@ __device__ __forceinline__ float fa_ex2(float x) {
   return y;
 }
 
-// One thread's half row of S (64 scores in TMEM at `ts`).  MASK: keys >= valid (relative to the half row) count as -inf.
+// One thread's half row of S (64 scores in TMEM at `ts`), read in four 16-column pieces through two register buffers: the next piece's
+// tcgen05.ld is in flight while the current one is processed (tcgen05.wait::ld waits for everything outstanding, so the load is issued
+// right after the wait).  MASK: keys >= valid (relative to the half row) count as -inf.
 template <bool MASK>
 __device__ __forceinline__ float fa_row_max(uint32_t ts, int valid) {      // max of the raw scores (the scale is positive: applied by the caller)
   float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 2; c++) {
-    uint32_t v[32];
-    tmem_ld32(ts + c * 32, v);
-    tmem_ld_wait();
+  uint32_t v[2][16];
+  tmem_ld16(ts, v[0]);
 #pragma unroll
-    for (int i = 0; i < 32; i++)
-      if (!MASK || c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+  for (int c = 0; c < 4; c++) {
+    tmem_ld_wait();
+    if (c < 3) tmem_ld16(ts + (c + 1) * 16, v[(c + 1) & 1]);
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      if (!MASK || c * 16 + i < valid) mx = fmaxf(mx, __uint_as_float(v[c & 1][i]));
   }
   return mx;
 }
@@ -57,23 +74,24 @@ __device__ __forceinline__ float fa_row_max(uint32_t ts, int valid) {      // ma
 template <bool MASK>
 __device__ __forceinline__ float fa_row_exp(uint32_t ts, uint32_t p_row, uint32_t sw, float scale_log2e, float mx, int valid) {
   float sum = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 2; c++) {
-    uint32_t v[32];
-    tmem_ld32(ts + c * 32, v);
-    tmem_ld_wait();
-    uint32_t pk[16];
+  uint32_t v[2][16];
+  tmem_ld16(ts, v[0]);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float s0 = (!MASK || c * 32 + i < valid) ? fmaf(__uint_as_float(v[i]), scale_log2e, -mx) : -INFINITY;
-      const float s1 = (!MASK || c * 32 + i + 1 < valid) ? fmaf(__uint_as_float(v[i + 1]), scale_log2e, -mx) : -INFINITY;
+  for (int c = 0; c < 4; c++) {
+    tmem_ld_wait();
+    if (c < 3) tmem_ld16(ts + (c + 1) * 16, v[(c + 1) & 1]);
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float s0 = (!MASK || c * 16 + i < valid) ? fmaf(__uint_as_float(v[c & 1][i]), scale_log2e, -mx) : -INFINITY;
+      const float s1 = (!MASK || c * 16 + i + 1 < valid) ? fmaf(__uint_as_float(v[c & 1][i + 1]), scale_log2e, -mx) : -INFINITY;
       const float p0 = fa_ex2(s0), p1 = fa_ex2(s1);
       sum += p0 + p1;
       pk[i >> 1] = fa_pack(p0, p1);
     }
 #pragma unroll
-    for (int g = 0; g < 4; g++) {       // 16-byte unit u = c * 4 + g of the row, stored at u ^ (row & 7)
-      const uint32_t addr = p_row + ((((uint32_t)c * 4 + g) ^ sw) << 4);
+    for (int g = 0; g < 2; g++) {       // 16-byte unit u = c * 2 + g of the row, stored at u ^ (row & 7)
+      const uint32_t addr = p_row + ((((uint32_t)c * 2 + g) ^ sw) << 4);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]), "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3]) : "memory");
     }
   }
@@ -98,7 +116,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < FA_RING; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 256); mbar_init(bar_o, 1); mbar_init(bar_oread, 256);
+    mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 8); mbar_init(bar_o, 1); mbar_init(bar_oread, 8);   // one arrival per softmax warp: every arrival wakes the waiting MMA thread
     fence_barrier_init();
     tma_prefetch_desc(&tm_qk);
   }
@@ -135,8 +153,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
       for (int j = 0; j < nkb; j++) {
         {   // S = Q K^T.  S is free: P(j - 1) was complete (bar_p) before the previous P V product was issued
           const int t = 2 * j, slot = t % FA_RING, u = t / FA_RING;
+          FA_STAMP(16 * j + 8);
           mbar_wait(bar_full + 8 * slot, u & 1);
           tc_fence_after();
+          FA_STAMP(16 * j + 9);
           const uint32_t ka = s_ring + slot * FA_TILE;
 #pragma unroll
           for (int ks = 0; ks < 4; ks++)
@@ -146,10 +166,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
         }
         {   // O_blk = P V
           const int t = 2 * j + 1, slot = t % FA_RING, u = t / FA_RING;
+          FA_STAMP(16 * j + 10);
           mbar_wait(bar_p, j & 1);
+          FA_STAMP(16 * j + 11);
           mbar_wait(bar_full + 8 * slot, u & 1);
           if (j > 0) mbar_wait(bar_oread, (j - 1) & 1);
           tc_fence_after();
+          FA_STAMP(16 * j + 12);
           const uint32_t va = s_ring + slot * FA_TILE;
 #pragma unroll
           for (int kc = 0; kc < 2; kc++)
@@ -159,6 +182,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
                         (kc | ks) > 0);
           umma_commit(bar_empty + 8 * slot);
           umma_commit(bar_o);
+          FA_STAMP(16 * j + 13);
         }
       }
     }
@@ -177,14 +201,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
     for (int i = 0; i < 32; i++) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nkb; j++) {
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 0);
       if (lane == 0) mbar_wait(bar_s, j & 1);
       __syncwarp();
       tc_fence_after();
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 1);
       const int valid = N - j * 128 - half * 64;        // keys of this half row below N
       const float own = (valid >= 64 ? fa_row_max<false>(ts, valid) : fa_row_max<true>(ts, valid)) * scale_log2e;
       float* x = xch + (j & 1) * 256;
       x[half * 128 + row] = own;
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 2);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 3);
       const float mx = fmaxf(m, fmaxf(own, x[(half ^ 1) * 128 + row]));
       const float c0 = fa_ex2(m - mx);                  // 0 on the first block
       const float sum = valid >= 64 ? fa_row_exp<false>(ts, p_row, sw, scale_log2e, mx, valid) : fa_row_exp<true>(ts, p_row, sw, scale_log2e, mx, valid);
@@ -192,11 +220,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
       m = mx;
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 4);
       // o = o * c0 + P V
       if (lane == 0) mbar_wait(bar_o, j & 1);
       __syncwarp();
       tc_fence_after();
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 5);
       {
         uint32_t v[32];
         tmem_ld32(to, v);
@@ -205,7 +236,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
         for (int i = 0; i < 32; i++) o[i] = fmaf(o[i], c0, __uint_as_float(v[i]));
       }
       tc_fence_before();
-      mbar_arrive(bar_oread);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_oread);
+      if (warp == 2 && lane == 0) FA_STAMP(16 * j + 6);
     }
     float* x = xch + (nkb & 1) * 256;                   // the buffer the last block did not use
     x[half * 128 + row] = l;
@@ -252,3 +285,10 @@ extern "C" int lvcb200_attention_tc(const void* qkv, int B, int N, int H, int he
                                                                                                    (__nv_bfloat16*)out);
   return check_launch("attention_tc_kernel");
 }
+
+#ifdef LVCB200_FA_TRACE
+extern "C" int lvcb200_debug_attention_trace(unsigned long long* host256) {
+  LVC_CUDA(cudaMemcpyFromSymbol(host256, g_fa_trace, sizeof(unsigned long long) * 256));
+  return 0;
+}
+#endif
