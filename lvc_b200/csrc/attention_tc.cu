@@ -131,58 +131,56 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, int N, int H, flo
     if (lane == 0) {   // ============================================================ TMA producer
       mbar_arrive_expect_tx(bar_q, FA_TILE);
       tma_load_2d(s_q, &tm_qk, bar_q, h * 64, row_base + q0);
+      uint32_t slot = 0, ph = 0;
       for (int j = 0; j < nkb; j++) {
-        {
-          const int t = 2 * j, slot = t % FA_RING, u = t / FA_RING;
-          mbar_wait(bar_empty + 8 * slot, (u & 1) ^ 1);
+#pragma unroll
+        for (int kv = 0; kv < 2; kv++) {           // K block j, then V block j: same rows of qkv, columns (1 + kv) * H * 64 + h * 64
+          mbar_wait(bar_empty + 8 * slot, ph ^ 1u);
           mbar_arrive_expect_tx(bar_full + 8 * slot, FA_TILE);
-          tma_load_2d(s_ring + slot * FA_TILE, &tm_qk, bar_full + 8 * slot, (H + h) * 64, row_base + j * 128);
-        }
-        {
-          const int t = 2 * j + 1, slot = t % FA_RING, u = t / FA_RING;
-          mbar_wait(bar_empty + 8 * slot, (u & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8 * slot, FA_TILE);
-          tma_load_2d(s_ring + slot * FA_TILE, &tm_qk, bar_full + 8 * slot, (2 * H + h) * 64, row_base + j * 128);
+          tma_load_2d(s_ring + slot * FA_TILE, &tm_qk, bar_full + 8 * slot, ((1 + kv) * H + h) * 64, row_base + j * 128);
+          if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ============================================================ MMA issuer
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128), idesc_o = make_idesc_bf16(128, 64) | (1u << 16);   // bit 16: B is MN-major
+      // One thread issues every MMA of the CTA and sits on the critical path of each key block (softmax -> P V -> next S): descriptors are
+      // built once and advanced by adding to their address field (16-byte units), ring slot / phase counters advance incrementally.
+      const uint64_t dq = make_smem_desc_sw128(s_q), dp = make_smem_desc_sw128(s_p), dr = make_smem_desc_sw128(s_ring);
+      uint32_t slot = 0, ph = 0;
       mbar_wait(bar_q, 0);
       for (int j = 0; j < nkb; j++) {
         {   // S = Q K^T.  S is free: P(j - 1) was complete (bar_p) before the previous P V product was issued
-          const int t = 2 * j, slot = t % FA_RING, u = t / FA_RING;
           FA_STAMP(16 * j + 8);
-          mbar_wait(bar_full + 8 * slot, u & 1);
+          mbar_wait(bar_full + 8 * slot, ph);
           tc_fence_after();
           FA_STAMP(16 * j + 9);
-          const uint32_t ka = s_ring + slot * FA_TILE;
+          const uint64_t dk = dr + (uint64_t)slot * (FA_TILE >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 4; ks++)
-            umma_bf16(t_s, make_smem_desc_sw128(s_q + ks * 32), make_smem_desc_sw128(ka + ks * 32), idesc_s, ks > 0);
+          for (int ks = 0; ks < 4; ks++) umma_bf16(t_s, dq + 2 * ks, dk + 2 * ks, idesc_s, ks > 0);      // 32 bytes per K step
           umma_commit(bar_empty + 8 * slot);
           umma_commit(bar_s);
+          if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
         }
         {   // O_blk = P V
-          const int t = 2 * j + 1, slot = t % FA_RING, u = t / FA_RING;
           FA_STAMP(16 * j + 10);
           mbar_wait(bar_p, j & 1);
           FA_STAMP(16 * j + 11);
-          mbar_wait(bar_full + 8 * slot, u & 1);
+          mbar_wait(bar_full + 8 * slot, ph);
           if (j > 0) mbar_wait(bar_oread, (j - 1) & 1);
           tc_fence_after();
           FA_STAMP(16 * j + 12);
-          const uint32_t va = s_ring + slot * FA_TILE;
+          const uint64_t dv = dr + (uint64_t)slot * (FA_TILE >> 4);
 #pragma unroll
           for (int kc = 0; kc < 2; kc++)
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)
-              umma_bf16(t_o, make_smem_desc_sw128(s_p + kc * FA_TILE + ks * 32), make_smem_desc_sw128(va + (kc * 4 + ks) * 2048), idesc_o,
-                        (kc | ks) > 0);
+            for (int ks = 0; ks < 4; ks++)     // A: 64-key half kc of P, 32 bytes per K step; B: 16 keys = 2 048 bytes per K step (MN-major)
+              umma_bf16(t_o, dp + kc * (FA_TILE >> 4) + 2 * ks, dv + (kc * 4 + ks) * 128, idesc_o, (kc | ks) > 0);
           umma_commit(bar_empty + 8 * slot);
           umma_commit(bar_o);
           FA_STAMP(16 * j + 13);
+          if (++slot == FA_RING) { slot = 0; ph ^= 1u; }
         }
       }
     }

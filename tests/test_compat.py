@@ -68,3 +68,37 @@ def test_build_model_returns_b200_architectures_and_state_dicts_interchange():
         m3.load_state_dict(r3, strict=True)
     finally:
         compat.uninstall()
+
+
+def test_layer_wrapper_mirrors_host_side():
+    """lvc_b200.layers mirrors of detectron2/layers (shape_spec.py, wrappers.py:14-118, batch_norm.py:13-135): construction, state-dict
+    names / versions, helper semantics, and loud refusal of what the GEMM path does not cover (no silent fallback)."""
+    import pytest
+    import torch
+    from lvc_b200 import _lib
+    from lvc_b200.layers import Conv2d, FrozenBatchNorm2d, Linear, ShapeSpec, cat, get_norm, nonzero_tuple
+    s = ShapeSpec(channels=256, stride=4)
+    assert s.channels == 256 and s.height is None and s._replace(stride=8).stride == 8
+    a = torch.arange(6).view(2, 3)
+    assert cat([a]) is a and cat([a, a], dim=1).shape == (2, 6)
+    assert [t.tolist() for t in nonzero_tuple(a > 2)] == [[1, 1, 1], [0, 1, 2]] and nonzero_tuple(torch.tensor(5))[0].tolist() == [0]
+    conv = Conv2d(64, 128, kernel_size=3, stride=1, padding=1, bias=False, norm=get_norm("FrozenBN", 128), activation=torch.nn.functional.relu)
+    assert sorted(conv.state_dict()) == ["norm.bias", "norm.running_mean", "norm.running_var", "norm.weight", "weight"]
+    assert FrozenBatchNorm2d._version == 3 and get_norm("", 8) is None
+    bn = FrozenBatchNorm2d(4)
+    old = {"weight": torch.ones(4), "bias": torch.zeros(4), "running_mean": torch.zeros(4), "running_var": torch.ones(4)}
+    meta = torch.nn.modules.module.OrderedDict()
+    old = torch.nn.modules.module.OrderedDict(old)
+    old._metadata = {"": {"version": 2}}
+    bn.load_state_dict(old)                                    # version 2 stored running_var + eps (batch_norm.py:78-84)
+    assert torch.allclose(bn.running_var, torch.ones(4) - 1e-5)
+    x = torch.randn(2, 4, 5, 5)
+    sc, sh = bn.scale_shift()
+    assert torch.allclose(bn(x), x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    with pytest.raises(_lib.LvcB200Error):
+        get_norm("BN", 8)
+    with pytest.raises(_lib.LvcB200Error):
+        Conv2d(3, 64, kernel_size=7, stride=2, padding=3)(torch.zeros(1, 3, 8, 8))      # unsupported shape: refused, not emulated
+    with pytest.raises(_lib.LvcB200Error):
+        conv(torch.zeros(1, 64, 8, 8))                                                  # CPU tensor: no CPU path
+    assert sorted(Linear(16, 8).state_dict()) == ["bias", "weight"]

@@ -284,3 +284,43 @@ def test_gemm_gelu_epilogue():
     _close(out, F.gelu(_ref_mm(a, w) + bias), True)
     with pytest.raises(Exception):
         ops.gemm(a, w[:64], bias=bias[:64], relu="gelu")           # narrow layers have no GELU instantiation
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 1.5e-2), ("strict", 5e-5)])
+def test_layer_wrappers_conv2d_linear_vs_torch(precision, tol):
+    """lvc_b200.layers.Conv2d / Linear (mirrors of detectron2/layers/wrappers.py:41-105 on the shift-GEMM) against torch's fp32 conv2d /
+    linear with the same parameters: 1x1 and 3x3, stride 1 and 2, FrozenBN folded, ReLU fused; relative L2 <= tol (bf16 operands: 1.5e-2,
+    strict pair operands: 5e-5; the reference values are computed in fp64)."""
+    import torch.nn.functional as F
+    from lvc_b200.layers import Conv2d, FrozenBatchNorm2d, Linear
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 64, 37, 45, generator=g).cuda()
+    for k, s, bn, act in [(1, 1, False, None), (3, 1, True, F.relu), (3, 2, True, torch.nn.ReLU()), (1, 2, False, torch.tanh)]:
+        norm = None
+        if bn:
+            norm = FrozenBatchNorm2d(96)
+            norm.weight.copy_(torch.rand(96, generator=g) + 0.5); norm.bias.copy_(torch.randn(96, generator=g) * 0.1)
+            norm.running_mean.copy_(torch.randn(96, generator=g) * 0.1); norm.running_var.copy_(torch.rand(96, generator=g) + 0.5)
+        conv = Conv2d(64, 96, kernel_size=k, stride=s, padding=k // 2, bias=not bn, norm=norm, activation=act).cuda()
+        conv.precision = precision
+        got = conv(x)
+        dd = lambda t: None if t is None else t.detach().double()       # fp64 reference (torch's fp32 CUDA conv may itself run in TF32)
+        want = F.conv2d(x.double(), dd(conv.weight), dd(conv.bias), stride=s, padding=k // 2)
+        if bn:
+            want = F.batch_norm(want, dd(norm.running_mean), dd(norm.running_var), dd(norm.weight), dd(norm.bias), False, 0.0, norm.eps)
+        if act is not None:
+            want = act(want)
+        assert got.shape == want.shape and got.dtype == x.dtype
+        rel = float((got.double() - want).norm() / want.norm())
+        assert rel <= tol, (k, s, bn, rel)
+        with torch.no_grad():
+            conv.weight.mul_(2.0)                        # in-place parameter change: the packed operands are rebuilt
+        want2 = F.conv2d(x.double(), dd(conv.weight), dd(conv.bias), stride=s, padding=k // 2)
+        if not bn and act is None:
+            assert float((conv(x).double() - want2).norm() / want2.norm()) <= tol
+    assert conv(x[:0]).shape == (0, 96, 19, 23)
+    lin = Linear(1024, 416).cuda()
+    lin.precision = precision
+    xf = torch.randn(3, 50, 1024, generator=g).cuda()
+    got, want = lin(xf), F.linear(xf.double(), lin.weight.detach().double(), lin.bias.detach().double())
+    assert got.shape == (3, 50, 416) and float((got.double() - want).norm() / want.norm()) <= tol
