@@ -382,12 +382,23 @@ rpn_nms_sweep_kernel(int topk, const unsigned long long* __restrict__ mask, cons
   {
     const uint4* src = reinterpret_cast<const uint4*>(mask + (size_t)slot0 * kMaskWords);
     uint4* dst = reinterpret_cast<uint4*>(smask);
-    for (int i = tid; i < n * kMaskWords / 2; i += blockDim.x) dst[i] = src[i];
+    const int nv = n * kMaskWords / 2;
+    for (int i0 = 0; i0 < nv; i0 += 8 * 256) {           // eight 16-byte loads in flight per thread (the copy is latency bound otherwise)
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = i0 + u * 256 + tid; if (i < nv) v[u] = src[i]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = i0 + u * 256 + tid; if (i < nv) dst[i] = v[u]; }
+    }
   }
-  if (tid < kMaskWords) validw[tid] = 0ull;
-  __syncthreads();
-  for (int j = tid; j < n; j += blockDim.x)
-    if (ws_valid[slot0 + j]) atomicOr(&validw[j >> 6], 1ull << (j & 63));
+  {   // validity bits by warp ballots (a 64-bit shared-memory atomicOr per box serialised 64 ways per word)
+    unsigned int* validw32 = reinterpret_cast<unsigned int*>(validw);
+    for (int j0 = 0; j0 < kMaxTopk; j0 += 256) {
+      const int j = j0 + tid;
+      const unsigned int b = __ballot_sync(0xffffffffu, j < n && ws_valid[slot0 + j] != 0);
+      if (lane == 0) validw32[j >> 5] = b;
+    }
+  }
   __syncthreads();
   if (wid == 0) {
     unsigned long long removed = 0ull;   // lane w (< 16) owns suppression word w
@@ -408,11 +419,17 @@ rpn_nms_sweep_kernel(int topk, const unsigned long long* __restrict__ mask, cons
       }
       kept = __shfl_sync(0xffffffffu, kept, 0);
       if (lane > c && lane < nchunks) {
+        // rows of the kept boxes OR-ed into this lane's word: the addresses depend on `kept` only, so four loads are issued per step
+        const unsigned long long* colw = smask + (size_t)(c * 64) * kMaskWords + lane;
         unsigned long long k = kept;
         while (k) {
-          int i = __ffsll((long long)k) - 1;
-          k &= k - 1;
-          removed |= smask[(size_t)(c * 64 + i) * kMaskWords + lane];
+          const int i0 = __ffsll((long long)k) - 1; k &= k - 1;
+          const int i1 = k ? __ffsll((long long)k) - 1 : i0; k &= k - 1;      // (k & (k - 1) of 0 is 0: exhausted lanes repeat i0)
+          const int i2 = k ? __ffsll((long long)k) - 1 : i0; k &= k - 1;
+          const int i3 = k ? __ffsll((long long)k) - 1 : i0; k &= k - 1;
+          const unsigned long long r0 = colw[(size_t)i0 * kMaskWords], r1 = colw[(size_t)i1 * kMaskWords],
+                                   r2 = colw[(size_t)i2 * kMaskWords], r3 = colw[(size_t)i3 * kMaskWords];
+          removed |= (r0 | r1) | (r2 | r3);
         }
       }
     }
@@ -443,36 +460,44 @@ __global__ void __launch_bounds__(256)
 rpn_merge_kernel(int n_levels, int post_topk, const float4* __restrict__ k_boxes, const float* __restrict__ k_scores,
                  const int* __restrict__ k_count, float4* __restrict__ proposals, float* __restrict__ prop_logits,
                  int32_t* __restrict__ counts) {
-  const int img = blockIdx.x;
+  // grid (n_levels, n_images): CTA (l, img) ranks level l's kept boxes among all levels of the image.  The (descending) score lists of
+  // the image are staged in shared memory once, so the four binary searches per box never leave the SM.
+  extern __shared__ float s_sc[];                         // [n_levels][kMaxTopk]
   __shared__ int cnt[kMaxLevels];
+  const int l = blockIdx.x, img = blockIdx.y;
   if (threadIdx.x < n_levels) cnt[threadIdx.x] = k_count[img * n_levels + threadIdx.x];
   __syncthreads();
   int total = 0;
-  for (int l = 0; l < n_levels; l++) total += cnt[l];
+  for (int l2 = 0; l2 < n_levels; l2++) {
+    total += cnt[l2];
+    const float* a = k_scores + (img * n_levels + l2) * kMaxTopk;
+    for (int p = threadIdx.x; p < cnt[l2]; p += blockDim.x) s_sc[l2 * kMaxTopk + p] = a[p];
+  }
+  __syncthreads();
   const int out_n = total < post_topk ? total : post_topk;
-  for (int l = 0; l < n_levels; l++) {
-    const int slot = (img * n_levels + l) * kMaxTopk;
-    for (int p = threadIdx.x; p < cnt[l]; p += blockDim.x) {
-      float s = k_scores[slot + p];
-      int rank = p;
-      for (int l2 = 0; l2 < n_levels; l2++) {
-        if (l2 == l) continue;
-        const float* a = k_scores + (img * n_levels + l2) * kMaxTopk;
-        int g = count_greater_desc(a, cnt[l2], s);
-        if (l2 < l) { while (g < cnt[l2] && a[g] == s) g++; }  // ties: lower level (lower concatenated index) first
-        rank += g;
-      }
-      if (rank < post_topk) {
-        proposals[(int64_t)img * post_topk + rank] = k_boxes[slot + p];
-        prop_logits[(int64_t)img * post_topk + rank] = s;
-      }
+  const int slot = (img * n_levels + l) * kMaxTopk;
+  for (int p = threadIdx.x; p < cnt[l]; p += blockDim.x) {
+    const float s = s_sc[l * kMaxTopk + p];
+    int rank = p;
+    for (int l2 = 0; l2 < n_levels; l2++) {
+      if (l2 == l) continue;
+      const float* a = s_sc + l2 * kMaxTopk;
+      int g = count_greater_desc(a, cnt[l2], s);
+      if (l2 < l) { while (g < cnt[l2] && a[g] == s) g++; }  // ties: lower level (lower concatenated index) first
+      rank += g;
+    }
+    if (rank < post_topk) {
+      proposals[(int64_t)img * post_topk + rank] = k_boxes[slot + p];
+      prop_logits[(int64_t)img * post_topk + rank] = s;
     }
   }
-  for (int r = out_n + threadIdx.x; r < post_topk; r += blockDim.x) {
-    proposals[(int64_t)img * post_topk + r] = make_float4(0, 0, 0, 0);
-    prop_logits[(int64_t)img * post_topk + r] = 0.f;
+  if (l == 0) {
+    for (int r = out_n + threadIdx.x; r < post_topk; r += blockDim.x) {
+      proposals[(int64_t)img * post_topk + r] = make_float4(0, 0, 0, 0);
+      prop_logits[(int64_t)img * post_topk + r] = 0.f;
+    }
+    if (threadIdx.x == 0) counts[img] = out_n;
   }
-  if (threadIdx.x == 0) counts[img] = out_n;
 }
 
 }  // namespace lvcb200
@@ -544,7 +569,7 @@ extern "C" int lvcb200_rpn_proposals(const lvcb200_rpn_level* levels, const lvcb
   }
   rc = check_launch("rpn_nms_sweep_kernel");
   if (rc) return rc;
-  rpn_merge_kernel<<<p->n_images, 256, 0, s>>>(p->n_levels, p->post_nms_topk, (const float4*)(ws + w.off_kboxes),
+  rpn_merge_kernel<<<dim3(p->n_levels, p->n_images), 256, p->n_levels * kMaxTopk * sizeof(float), s>>>(p->n_levels, p->post_nms_topk, (const float4*)(ws + w.off_kboxes),
                                                (const float*)(ws + w.off_kscores), (const int*)(ws + w.off_kcount),
                                                (float4*)proposals, prop_logits, counts);
   return check_launch("rpn_merge_kernel");
