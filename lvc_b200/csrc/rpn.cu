@@ -70,21 +70,25 @@ __device__ __forceinline__ bool rpn_scan_range(const RpnLevels& L, int n_levels,
   return beg < n;
 }
 
-// digit (from the top) at which the suffix count of hist reaches `need`; returns digit, writes count strictly above it
+// digit (from the top) at which the suffix count of hist reaches `need`; returns digit, writes count strictly above it.
+// The 2048-bin histogram is staged in shared memory first (coalesced): every CTA of the scan kernels runs this, and walking the bins in
+// global memory (64 strided loads per lane, then a serial walk) cost ~15 us per call -- more than the CTA's own 2048-anchor scan.
 __device__ __forceinline__ int rpn_find_digit(const unsigned int* __restrict__ hist, unsigned int need, unsigned int* above_out,
-                                              unsigned int* s_tmp /* 2 words smem */) {
+                                              unsigned int* s_tmp /* 2 words smem */, unsigned int* s_hist /* 2048 words smem */) {
   const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_hist[i] = hist[i];
+  __syncthreads();
   if (threadIdx.x < 32) {
     const int per = 64;
     unsigned int local = 0;
-    for (int b = 0; b < per; b++) local += hist[lane * per + b];
+    for (int b = 0; b < per; b++) local += s_hist[lane * per + ((b + lane) & (per - 1))];   // rotated: bank-conflict free
     unsigned int suffix = local;
     for (int o = 1; o < 32; o <<= 1) { unsigned int v = __shfl_down_sync(0xffffffffu, suffix, o); if (lane + o < 32) suffix += v; }
     unsigned int above = suffix - local;
     if (above < need && suffix >= need) {
       unsigned int acc = above; int d = 0;
       for (int b = per - 1; b >= 0; b--) {
-        unsigned int h = hist[lane * per + b];
+        unsigned int h = s_hist[lane * per + b];
         if (acc + h >= need) { d = lane * per + b; break; }
         acc += h;
       }
@@ -114,7 +118,7 @@ rpn_hist1_kernel(RpnLevels L, int n_levels, unsigned int* __restrict__ hist1) {
 
 __global__ void __launch_bounds__(256)
 rpn_hist2_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __restrict__ hist1, unsigned int* __restrict__ hist2) {
-  __shared__ unsigned int h[2048];
+  __shared__ unsigned int h[2048], sh[2048];
   __shared__ unsigned int tmp[2];
   int img, lvl, beg, end;
   if (!rpn_scan_range(L, n_levels, img, lvl, beg, end)) return;
@@ -123,7 +127,7 @@ rpn_hist2_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __rest
   const unsigned int k = (unsigned)(topk < n ? topk : n);
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) h[i] = 0u;
   unsigned int above;
-  const unsigned int d1 = (unsigned)rpn_find_digit(hist1 + (size_t)(img * n_levels + lvl) * 2048, k, &above, tmp);
+  const unsigned int d1 = (unsigned)rpn_find_digit(hist1 + (size_t)(img * n_levels + lvl) * 2048, k, &above, tmp, sh);
   const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
   for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
     unsigned int key = float_to_ordered(__ldg(logits + rpn_addr(i, lv.A, lv.W, lv.row_stride_l, lv.pix_stride_l, 1)));
@@ -137,7 +141,7 @@ rpn_hist2_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __rest
 __global__ void __launch_bounds__(256)
 rpn_collect_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __restrict__ hist1, const unsigned int* __restrict__ hist2,
                    unsigned int* __restrict__ ccount, unsigned long long* __restrict__ cand) {
-  __shared__ unsigned int tmp[2];
+  __shared__ unsigned int tmp[2], sh[2048];
   int img, lvl, beg, end;
   if (!rpn_scan_range(L, n_levels, img, lvl, beg, end)) return;
   const lvcb200_rpn_level& lv = L.lv[lvl];
@@ -145,9 +149,9 @@ rpn_collect_kernel(RpnLevels L, int n_levels, int topk, const unsigned int* __re
   const unsigned int k = (unsigned)(topk < n ? topk : n);
   const int slot = img * n_levels + lvl;
   unsigned int above1, above2;
-  const unsigned int d1 = (unsigned)rpn_find_digit(hist1 + (size_t)slot * 2048, k, &above1, tmp);
+  const unsigned int d1 = (unsigned)rpn_find_digit(hist1 + (size_t)slot * 2048, k, &above1, tmp, sh);
   __syncthreads();
-  const unsigned int d2 = (unsigned)rpn_find_digit(hist2 + (size_t)slot * 2048, k - above1, &above2, tmp);
+  const unsigned int d2 = (unsigned)rpn_find_digit(hist2 + (size_t)slot * 2048, k - above1, &above2, tmp, sh);
   const unsigned int t22 = (d1 << 11) | d2;   // every key with a 22-bit prefix >= t22 is a candidate (>= k of them)
   const float* logits = lv.logits + (int64_t)img * lv.img_stride_l;
   const int lane = threadIdx.x & 31;
