@@ -9,7 +9,8 @@ The reference mines pseudo-labels with three tools run one after the other, each
 
 ``PseudoLabelMiner`` chains the same operators on the device for one batch: the detector's output block stays in HBM, the
 candidate filter runs on it, the crops are cut from the device-resident detector input (the image ``DatasetMapperQE`` would
-re-load and resize the same way), the descriptors go straight into the kNN verifier, and the corrector reads the same images.
+re-load and resize the same way), the descriptors go straight into the kNN verifier, and the corrector reads the same images
+(only those that kept a pseudo-label, like the reference's corrector data set).
 One packed D2H (detections + flags) is the only host round trip before the final result; it is needed because the number of
 candidates sizes the ViT batch.
 
@@ -153,16 +154,48 @@ class PseudoLabelMiner:
             res = self.bank.verify(feats, qcls, topk=10, knn=self.knn)
             D = feats.shape[1]
             out = torch.cat([feats, res["votes"].float(), res["keep"].float()[:, None]], dim=1)       # [total, D + 10 + 1], one D2H
-            if self.corrector is not None:
-                # train_net_reg_qe.py --eval-only (GeneralizedRCNNRegOnly.inference, rcnn.py:372-410) on the same device images.  The
-                # heads run on every candidate (their count is known here without another round trip); only the verified rows are used.
-                pyramid, _ = self.corrector.engine.run_features(images)
-                planes = [pyramid[l] for l in (2, 3, 4, 5)]
-                reg = self.corrector.head(planes, [torch.from_numpy(c[1]).reshape(-1, 4).to(dev, non_blocking=True) for c in cand], sizes)
-                out = torch.cat([out, torch.cat(reg)], dim=1)
             hout = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
             hout.copy_(out, non_blocking=True)
             st.update(out=hout, D=D)
+        st["done"] = torch.cuda.current_stream(dev).record_event()
+        return st
+
+    def _correct(self, st):
+        """train_net_reg_qe.py --eval-only (GeneralizedRCNNRegOnly.inference, rcnn.py:372-410) on the verified boxes.  Like the reference,
+        whose corrector data set holds only the images that kept a pseudo-label, the corrector's backbone runs on those images only: the
+        sub-batch is padded (by repeating its first image) to the next power of two so that the engine keeps at most log2(batch) + 1
+        activation sets per image shape."""
+        st["done"].synchronize()
+        dev = self.detector._device
+        cand, m, total, images, sizes = st["cand"], st["m"], st["total"], st["images"], st["sizes"]
+        st["corr"] = None
+        if self.corrector is None or not total:
+            return st
+        D = st["D"]
+        keep = st["out"][:, D + 10].bool()
+        off, idx, kept = 0, [], []
+        for i, (sel, fb, win) in enumerate(cand):
+            kb = keep[off:off + m[i]].numpy()
+            off += m[i]
+            if kb.any():
+                idx.append(i)
+                kept.append(torch.from_numpy(fb[kb]).reshape(-1, 4))
+        if not idx:
+            return st
+        nb = 1
+        while nb < len(idx):
+            nb *= 2
+        nb = min(nb, max(len(images), len(idx)))
+        pad = nb - len(idx)
+        sub_images = [images[i] for i in idx] + [images[idx[0]]] * pad
+        sub_sizes = [sizes[i] for i in idx] + [sizes[idx[0]]] * pad
+        pyramid, _ = self.corrector.engine.run_features(sub_images)
+        planes = [pyramid[l] for l in (2, 3, 4, 5)]
+        boxes = [b.to(dev, non_blocking=True) for b in kept] + [torch.zeros((0, 4), device=dev)] * pad
+        reg = torch.cat(self.corrector.head(planes, boxes, sub_sizes))
+        hreg = torch.empty(reg.shape, dtype=torch.float32, pin_memory=True)
+        hreg.copy_(reg, non_blocking=True)
+        st["corr"] = (idx, [len(b) for b in kept], hreg)
         st["done"] = torch.cuda.current_stream(dev).record_event()
         return st
 
@@ -173,6 +206,13 @@ class PseudoLabelMiner:
         D = st.get("D", getattr(self.bank, "D", 0))
         off = 0
         verified = 0
+        corrected = {}
+        if st.get("corr") is not None:
+            idx, lens, hreg = st["corr"]
+            o2 = 0
+            for i, n_i in zip(idx, lens):
+                corrected[i] = hreg[o2:o2 + n_i]
+                o2 += n_i
         for i, (sel, fb, win) in enumerate(cand):
             inst, o = results[i]["instances"], outs[i]
             ci = Instances(sizes[i])
@@ -180,7 +220,7 @@ class PseudoLabelMiner:
             ci.gt_classes = inst.pred_classes[sel]
             ci.scores = inst.scores[sel]
             ci.det_index = sel
-            rows = hout[off:off + m[i]] if total else torch.zeros((0, D + 15))
+            rows = hout[off:off + m[i]] if total else torch.zeros((0, D + 11))
             ci.crop_feats = rows[:, :D].clone()
             ci.top10_shots = rows[:, D:D + 10].to(torch.int64)
             ci.keep = rows[:, D + 10].to(torch.int64)
@@ -189,8 +229,8 @@ class PseudoLabelMiner:
             kb = ci.keep.bool()
             verified += int(kb.sum())
             pl = Instances(o)
-            if self.corrector is not None and total:
-                b = rows[:, D + 11:D + 15][kb].clone()
+            if i in corrected:
+                b = corrected[i].clone()
                 b[:, 0::2] *= o[1] / sizes[i][1]                              # detector_postprocess, postprocessing.py:37-59
                 b[:, 1::2] *= o[0] / sizes[i][0]
                 bx = Boxes(b)
@@ -206,14 +246,14 @@ class PseudoLabelMiner:
 
     @torch.no_grad()
     def __call__(self, batched_inputs: List[dict]) -> List[dict]:
-        return self._finish(self._verify(self._label(batched_inputs)))
+        return self._finish(self._correct(self._verify(self._label(batched_inputs))))
 
     @torch.no_grad()
     def stream(self, batches):
         """``miner(inputs)`` for every batch of the iterable, in order, software-pipelined: while the GPU runs the detector on batch i
         the host selects the candidates of batch i - 1 and enqueues their crops / ViT / kNN behind it, and assembles the result of
         batch i - 2 -- no stage waits for the device with nothing queued behind it.  The H2D copy of the next batch runs on a copy
-        stream, into persistent device image sets (three batches are in flight: five sets per shape)."""
+        stream, into persistent device image sets (four batches are in flight -- label, verify, correct, assemble: six sets per shape)."""
         from collections import deque
         dev = self.detector._device
         main, copy_stream = torch.cuda.current_stream(dev), torch.cuda.Stream(device=dev)
@@ -224,16 +264,16 @@ class PseudoLabelMiner:
             if ring is None:
                 while len(self._img_ring) >= 3:
                     self._img_ring.pop(next(iter(self._img_ring)))
-                ring = self._img_ring[key] = {"sets": [[torch.empty(sh, dtype=dt, device=dev) for sh, dt in key] for _ in range(5)],
-                                              "free": [None] * 5, "n": 0}
+                ring = self._img_ring[key] = {"sets": [[torch.empty(sh, dtype=dt, device=dev) for sh, dt in key] for _ in range(6)],
+                                              "free": [None] * 6, "n": 0}
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_stream(main)               # new blocks may recycle memory a queued kernel still reads
-            slot = ring["n"] % 5
+            slot = ring["n"] % 6
             ring["n"] += 1
             images = ring["sets"][slot]
             with torch.cuda.stream(copy_stream):
                 if ring["free"][slot] is not None:
-                    copy_stream.wait_event(ring["free"][slot])  # the set's previous user (five batches ago) has been verified
+                    copy_stream.wait_event(ring["free"][slot])  # the set's previous user (six batches ago) is through the corrector
                 for dst, x in zip(images, batched_inputs):
                     dst.copy_(x["image"], non_blocking=True)
                 ready = copy_stream.record_event()
@@ -242,8 +282,8 @@ class PseudoLabelMiner:
         it = iter(batches)
         nxt = next(it, None)
         staged = stage(nxt) if nxt is not None else None
-        labelled, verified = deque(), deque()
-        while staged is not None or labelled or verified:
+        labelled, verified, corrected = deque(), deque(), deque()
+        while staged is not None or labelled or verified or corrected:
             if staged is not None:
                 batched_inputs, images, ready, ring = staged
                 nxt = next(it, None)
@@ -253,7 +293,10 @@ class PseudoLabelMiner:
                 staged = staged_next
             if labelled and (len(labelled) > 1 or staged is None):
                 st, ring = labelled.popleft()
-                verified.append(self._verify(st))
-                ring[0]["free"][ring[1]] = st["done"]
+                verified.append((self._verify(st), ring))
             if verified and (len(verified) > 1 or (staged is None and not labelled)):
-                yield self._finish(verified.popleft())
+                st, ring = verified.popleft()
+                corrected.append(self._correct(st))
+                ring[0]["free"][ring[1]] = st["done"]          # the image set is free once the corrector (its last reader) has run
+            if corrected and (len(corrected) > 1 or (staged is None and not labelled and not verified)):
+                yield self._finish(corrected.popleft())
