@@ -1,2 +1,2 @@
 """lvc_b200: Blackwell-native pseudo-label mining hot path of prannaykaul/lvc."""
-__version__ = "0.1.0"
+__version__ = "0.2.0"
