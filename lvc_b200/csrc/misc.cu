@@ -302,6 +302,40 @@ __global__ void crops_qe_kernel(const T* __restrict__ img, int H, int W, const C
   }
 }
 
+// S % 4 == 0 fast path: grid (ceil(S * S / 4 / 256), 3, boxes): a thread produces four neighbouring output pixels of one (box, channel)
+// plane (one 16-byte store); the box geometry, the two fp32 scale divisions and the row's source line are computed once per thread instead of
+// once per pixel, and no 64-bit index arithmetic is left.  Same arithmetic per pixel as crops_qe_kernel: identical output.
+template <typename T>
+__global__ void __launch_bounds__(256)
+crops_qe4_kernel(const T* __restrict__ img, int H, int W, const CropGeom* __restrict__ geom, int n, int S,
+                 const float* __restrict__ mean, const float* __restrict__ inv_std, float* __restrict__ out) {
+  const int q4 = S >> 2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S * q4) return;
+  const int oy = t / q4, ox0 = (t - oy * q4) * 4;
+  const int c = blockIdx.y;
+  const float m = mean != nullptr ? mean[c] : 0.f, is = mean != nullptr ? inv_std[c] : 1.f;
+  for (int b = blockIdx.z; b < n; b += gridDim.z) {
+    const CropGeom g = geom[b];
+    const float sy = (float)g.Hp / (float)S, sx = (float)g.Wp / (float)S;
+    int py = (int)floorf((float)oy * sy); py = py < g.Hp - 1 ? py : g.Hp - 1;
+    const int cy = py - g.tp;
+    const bool row_in = cy >= 0 && cy < g.ah;
+    const T* line = img + ((long long)c * H + g.y0 + (row_in ? cy : 0)) * W + g.x0;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      int px = (int)floorf((float)(ox0 + e) * sx); px = px < g.Wp - 1 ? px : g.Wp - 1;
+      const int cx = px - g.lp;
+      float x = 0.f;
+      if (row_in && cx >= 0 && cx < g.aw) x = (float)line[cx];
+      if (mean != nullptr) x = (x - m) * is;
+      v[e] = x;
+    }
+    *reinterpret_cast<float4*>(out + (((long long)b * 3 + c) * S + oy) * S + ox0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 }  // namespace lvcb200
 
 using namespace lvcb200;
@@ -430,6 +464,14 @@ extern "C" int lvcb200_crops_qe(const void* image, int image_dtype, int H, int W
   if (n == 0) return 0;
   LVC_REQUIRE(image && geom && out && H > 0 && W > 0 && S > 0, "crops_qe: bad argument");
   LVC_REQUIRE((mean == nullptr) == (inv_std == nullptr), "crops_qe: mean and inv_std go together");
+  if (S % 4 == 0 && S <= 4096 && ((uintptr_t)out % 16) == 0 && (image_dtype == LVCB200_U8 || image_dtype == LVCB200_F32)) {
+    const dim3 grid((unsigned)((S * (S / 4) + 255) / 256), 3, (unsigned)(n < 32768 ? n : 32768));
+    if (image_dtype == LVCB200_U8)
+      crops_qe4_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)image, H, W, (const CropGeom*)geom, n, S, mean, inv_std, out);
+    else
+      crops_qe4_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)image, H, W, (const CropGeom*)geom, n, S, mean, inv_std, out);
+    return check_launch("crops_qe4_kernel");
+  }
   long long total = (long long)n * 3 * S * S;
   if (image_dtype == LVCB200_U8)
     crops_qe_kernel<unsigned char><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)image, H, W, (const CropGeom*)geom, n, S, mean, inv_std, out);

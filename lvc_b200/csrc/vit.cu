@@ -41,6 +41,59 @@ __global__ void vit_assemble_kernel(const __nv_bfloat16* __restrict__ patch_toke
   }
 }
 
+// patch 8 fast path: one thread per (patch, channel, patch row): eight contiguous pixels in (two float4), eight bf16 out (one 16-byte store);
+// consecutive threads walk the 24 (channel, row) pairs of a patch, so a patch's 384-byte output row is written by 24 neighbouring threads.
+__global__ void __launch_bounds__(256)
+vit_patchify8_kernel(const float* __restrict__ crops, int B, int S, __nv_bfloat16* __restrict__ out) {
+  const int gp = S >> 3;
+  const long long total = (long long)B * gp * gp * 24;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ciy = (int)(i % 24);
+    const long long row = i / 24;
+    const int c = ciy >> 3, iy = ciy & 7;
+    const int px = (int)(row % gp), py = (int)((row / gp) % gp);
+    const long long b = row / ((long long)gp * gp);
+    const float4* src = reinterpret_cast<const float4*>(crops + ((b * 3 + c) * S + py * 8 + iy) * S + px * 8);
+    const float4 a = __ldg(src), d = __ldg(src + 1);
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+    h[0] = __floats2bfloat162_rn(a.x, a.y); h[1] = __floats2bfloat162_rn(a.z, a.w);
+    h[2] = __floats2bfloat162_rn(d.x, d.y); h[3] = __floats2bfloat162_rn(d.z, d.w);
+    *reinterpret_cast<uint4*>(out + row * 192 + ciy * 8) = o;
+  }
+}
+
+// D % 8 == 0 fast path of vit_assemble: eight channels (16 bytes) per thread.
+__global__ void __launch_bounds__(256)
+vit_assemble8_kernel(const __nv_bfloat16* __restrict__ patch_tokens, const float* __restrict__ cls_token, const float* __restrict__ pos_embed,
+                     int B, int Np, int D, __nv_bfloat16* __restrict__ x) {
+  const int dv = D >> 3;
+  const long long total = (long long)B * (Np + 1) * dv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % dv) * 8;
+    const long long tok = i / dv;
+    const int t = (int)(tok % (Np + 1));
+    const long long b = tok / (Np + 1);
+    float v[8];
+    if (t == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = cls_token[d + e];
+    } else {
+      const uint4 u = *reinterpret_cast<const uint4*>(patch_tokens + (b * Np + t - 1) * D + d);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    }
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos_embed + (long long)t * D + d));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos_embed + (long long)t * D + d + 4));
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+    ho[0] = __floats2bfloat162_rn(v[0] + p0.x, v[1] + p0.y); ho[1] = __floats2bfloat162_rn(v[2] + p0.z, v[3] + p0.w);
+    ho[2] = __floats2bfloat162_rn(v[4] + p1.x, v[5] + p1.y); ho[3] = __floats2bfloat162_rn(v[6] + p1.z, v[7] + p1.w);
+    *reinterpret_cast<uint4*>(x + tok * D + d) = o;
+  }
+}
+
 template <typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int D, long long ldx, const float* __restrict__ gamma,
@@ -65,6 +118,38 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int D, lon
     const float a = (v.x - mean) * rstd * gamma[d] + beta[d], b = (v.y - mean) * rstd * gamma[d + 1] + beta[d + 1];
     if constexpr (sizeof(TO) == 2) *reinterpret_cast<__nv_bfloat162*>(o + d) = __floats2bfloat162_rn(a, b);
     else { o[d] = a; o[d + 1] = b; }
+  }
+}
+
+// Same, for D = 64 * NP with the row held in registers (one read of x instead of two): warp per row, lane l owns the bf16 pairs at
+// d = 2 l + 64 i.  gamma / beta are read through the read-only path (the same 3 KB for every row).
+template <typename TO, int NP>
+__global__ void __launch_bounds__(256)
+layernorm_reg_kernel(const __nv_bfloat16* __restrict__ x, long long rows, long long ldx, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, TO* __restrict__ out, long long ldo) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* p = x + row * ldx + 2 * lane;
+  float2 v[NP];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NP; i++) v[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + 64 * i));
+#pragma unroll
+  for (int i = 0; i < NP; i++) { s += v[i].x + v[i].y; s2 += v[i].x * v[i].x + v[i].y * v[i].y; }
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  constexpr float inv_d = 1.0f / (float)(64 * NP);
+  const float mean = s * inv_d;
+  const float var = fmaxf(s2 * inv_d - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  TO* o = out + row * ldo + 2 * lane;
+#pragma unroll
+  for (int i = 0; i < NP; i++) {
+    const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + 2 * lane + 64 * i));
+    const float2 b = __ldg(reinterpret_cast<const float2*>(beta + 2 * lane + 64 * i));
+    const float a0 = (v[i].x - mean) * rstd * g.x + b.x, a1 = (v[i].y - mean) * rstd * g.y + b.y;
+    if constexpr (sizeof(TO) == 2) *reinterpret_cast<__nv_bfloat162*>(o + 64 * i) = __floats2bfloat162_rn(a0, a1);
+    else { o[64 * i] = a0; o[64 * i + 1] = a1; }
   }
 }
 
@@ -224,6 +309,11 @@ static inline unsigned vit_grid(long long total, int threads) {
 extern "C" int lvcb200_vit_patchify(const float* crops, int B, int S, int patch, void* out, void* stream) {
   if (B == 0) return 0;
   LVC_REQUIRE(crops && out && S > 0 && patch > 0 && S % patch == 0, "vit_patchify: bad argument");
+  if (patch == 8 && S % 8 == 0 && ((uintptr_t)crops % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+    const long long n = (long long)B * (S / 8) * (S / 8) * 24;
+    vit_patchify8_kernel<<<vit_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(crops, B, S, (__nv_bfloat16*)out);
+    return check_launch("vit_patchify8_kernel");
+  }
   const long long total = (long long)B * (S / patch) * (S / patch) * 3 * patch * patch;
   vit_patchify_kernel<<<vit_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(crops, B, S, patch, (__nv_bfloat16*)out);
   return check_launch("vit_patchify_kernel");
@@ -233,6 +323,12 @@ extern "C" int lvcb200_vit_assemble(const void* patch_tokens, const float* cls_t
                                     void* stream) {
   if (B == 0) return 0;
   LVC_REQUIRE(patch_tokens && cls_token && pos_embed && x && Np > 0 && D > 0, "vit_assemble: bad argument");
+  if (D % 8 == 0 && ((uintptr_t)patch_tokens % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)pos_embed % 16) == 0) {
+    const long long n = (long long)B * (Np + 1) * (D / 8);
+    vit_assemble8_kernel<<<vit_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)patch_tokens, cls_token, pos_embed, B, Np, D,
+                                                                          (__nv_bfloat16*)x);
+    return check_launch("vit_assemble8_kernel");
+  }
   const long long total = (long long)B * (Np + 1) * D;
   vit_assemble_kernel<<<vit_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)patch_tokens, cls_token, pos_embed, B, Np, D,
                                                                             (__nv_bfloat16*)x);
@@ -244,6 +340,13 @@ extern "C" int lvcb200_layernorm(const void* x, int64_t rows, int D, int64_t ldx
   if (rows == 0) return 0;
   LVC_REQUIRE(x && gamma && beta && out && D > 0 && D % 2 == 0 && ldx % 2 == 0 && ldo % 2 == 0, "layernorm: bad argument (D, pitches must be even)");
   const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
+  if (D == 384 && ((uintptr_t)gamma % 8) == 0 && ((uintptr_t)beta % 8) == 0 && (out_dtype == LVCB200_BF16 || out_dtype == LVCB200_F32)) {   // ViT-S
+    if (out_dtype == LVCB200_BF16)
+      layernorm_reg_kernel<__nv_bfloat16, 6><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, ldx, gamma, beta, eps, (__nv_bfloat16*)out, ldo);
+    else
+      layernorm_reg_kernel<float, 6><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, ldx, gamma, beta, eps, (float*)out, ldo);
+    return check_launch("layernorm_reg_kernel");
+  }
   if (out_dtype == LVCB200_BF16)
     layernorm_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, D, ldx, gamma, beta, eps, (__nv_bfloat16*)out, ldo);
   else if (out_dtype == LVCB200_F32)

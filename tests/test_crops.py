@@ -40,3 +40,10 @@ def test_kernel_matches_reference_and_normalises(golden, op):
     torch.testing.assert_close(nrm, want, rtol=1e-5, atol=1e-5)
     big = get_crops_qe(img, g["boxes"], op, size=224)                               # the reference's real crop size
     assert np.array_equal(big.cpu().numpy(), O.get_crops_qe(g["img"], g["boxes"], op, 224))
+    odd = get_crops_qe(img, g["boxes"], op, size=30)                                # size % 4 != 0: the generic (per-pixel) kernel
+    assert np.array_equal(odd.cpu().numpy(), O.get_crops_qe(g["img"], g["boxes"], op, 30))
+    odd_n = get_crops_qe(img, g["boxes"], op, size=30, mean=mean, std=std)
+    inv = (1.0 / torch.tensor(std)).view(1, 3, 1, 1).cuda()
+    assert torch.equal(odd_n, (odd - torch.tensor(mean).view(1, 3, 1, 1).cuda()) * inv)   # the same (x - mean) * (1 / std) in both kernels
+    fast_n = get_crops_qe(img, g["boxes"], op, size=32, mean=mean, std=std)
+    assert torch.equal(fast_n, (got - torch.tensor(mean).view(1, 3, 1, 1).cuda()) * inv)

@@ -64,6 +64,11 @@ def test_layernorm_and_gelu_kernels():
     ob = torch.empty((10, 384), dtype=torch.bfloat16, device=DEV)
     _lib.check(lib.lvcb200_layernorm(_lib.ptr(x), 10, 384, 100 * 384, _lib.ptr(gam), _lib.ptr(bet), 1e-6, _lib.ptr(ob), _lib.BF16, 384, _lib.stream_ptr()), "ln")
     torch.testing.assert_close(ob.float(), F.layer_norm(x.float()[::100], (384,), gam, bet, 1e-6), rtol=2 ** -7, atol=2e-2)
+    # another width takes the generic (two-pass) kernel
+    x2 = (torch.randn(77, 256, generator=g) * 2 - 1).bfloat16().to(DEV)
+    o2 = torch.empty((77, 256), dtype=torch.float32, device=DEV)
+    _lib.check(lib.lvcb200_layernorm(_lib.ptr(x2), 77, 256, 256, _lib.ptr(gam), _lib.ptr(bet), 1e-6, _lib.ptr(o2), _lib.F32, 256, _lib.stream_ptr()), "ln")
+    torch.testing.assert_close(o2, F.layer_norm(x2.float(), (256,), gam[:256], bet[:256], 1e-6), rtol=1e-4, atol=1e-4)
     y = x.clone().view(-1)
     _lib.check(lib.lvcb200_gelu(_lib.ptr(y), y.numel(), _lib.stream_ptr()), "gelu")
     torch.testing.assert_close(y.view_as(x).float(), F.gelu(x.float()), rtol=2 ** -7, atol=1e-3)
@@ -113,3 +118,25 @@ def test_crops_to_descriptors_to_knn_stays_on_device(golden):
     gi, wi = res["top_idx"].cpu().numpy()[:, 0], w["top_idx"][:, 0]
     close = (w["top_sim"][:, 0] - w["top_sim"][:, 1]) < 2e-2
     assert np.all((gi == wi) | close)
+
+
+def test_patchify_and_assemble_kernels_exact():
+    """vit_patchify (crops -> patch rows in the conv weight's (c, iy, ix) column order) and vit_assemble ([cls | tokens] + pos_embed), fast
+    (patch 8 / D % 8 == 0) and generic paths, against the same rearrangement in torch: identical bf16 values."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(12)
+    for S, P in [(224, 8), (64, 8), (48, 16)]:
+        B, gp = 3, S // P
+        crops = torch.randn(B, 3, S, S, generator=g).to(DEV)
+        out = torch.empty((B * gp * gp, 3 * P * P), dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.lvcb200_vit_patchify(_lib.ptr(crops), B, S, P, _lib.ptr(out), _lib.stream_ptr()), "patchify")
+        want = crops.view(B, 3, gp, P, gp, P).permute(0, 2, 4, 1, 3, 5).reshape(B * gp * gp, 3 * P * P).bfloat16()
+        assert torch.equal(out, want), (S, P)
+    for D in (384, 36):
+        B, Np = 2, 49
+        tok = torch.randn(B * Np, D, generator=g).bfloat16().to(DEV)
+        cls, pos = torch.randn(D, generator=g).to(DEV), torch.randn(Np + 1, D, generator=g).to(DEV)
+        x = torch.empty((B * (Np + 1), D), dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.lvcb200_vit_assemble(_lib.ptr(tok), _lib.ptr(cls), _lib.ptr(pos), B, Np, D, _lib.ptr(x), _lib.stream_ptr()), "assemble")
+        full = torch.cat([cls.view(1, 1, D).expand(B, 1, D), tok.float().view(B, Np, D)], dim=1) + pos.view(1, Np + 1, D)
+        assert torch.equal(x, full.bfloat16().view(-1, D)), D
