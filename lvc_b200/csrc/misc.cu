@@ -122,6 +122,20 @@ __global__ void maxpool_s2d_kernel(const uint4* __restrict__ in, int n, int Ho, 
 }
 
 // out[n, oy, ox] = in[n, 2*oy, 2*ox]  (1x1 stride-2 conv input side; LastLevelMaxPool k=1 s=2)
+// grid (ceil((Wo + 2) * CV / 256), n * (Ho + 2)): a block row per output plane row, 32-bit index arithmetic only (the grid-stride form
+// below spends ~100 instructions of 64-bit division per 16-byte vector).
+__global__ void __launch_bounds__(256)
+subsample2_rows_kernel(const uint4* __restrict__ in, int H, int W, int CV, uint4* __restrict__ out, int Ho, int Wo) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (Wo + 2) * CV) return;
+  const int px = t / CV, cv = t - px * CV;
+  const int row = blockIdx.y, img = row / (Ho + 2), py = row - img * (Ho + 2);
+  uint4 r = make_uint4(0, 0, 0, 0);
+  if (py >= 1 && py <= Ho && px >= 1 && px <= Wo)
+    r = __ldg(in + (((long long)img * (H + 2) + 2 * py - 1) * (W + 2) + 2 * px - 1) * CV + cv);
+  out[((long long)row * (Wo + 2) + px) * CV + cv] = r;
+}
+
 __global__ void subsample2_kernel(const uint4* __restrict__ in, int n, int H, int W, int CV, uint4* __restrict__ out, int Ho, int Wo) {
   const long long total = (long long)n * (Ho + 2) * (Wo + 2) * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -446,6 +460,11 @@ extern "C" int lvcb200_maxpool_s2d(const void* in, int n, int Ho, int Wo, int C,
 extern "C" int lvcb200_subsample2(const void* in, int n, int H, int W, int C, void* out, void* stream) {
   LVC_REQUIRE(n >= 1 && H >= 1 && W >= 1 && C % 8 == 0 && in && out, "subsample2: bad argument");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  if ((long long)n * (Ho + 2) <= 65535) {
+    const dim3 grid((unsigned)(((Wo + 2) * (C / 8) + 255) / 256), (unsigned)(n * (Ho + 2)));
+    subsample2_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)in, H, W, C / 8, (uint4*)out, Ho, Wo);
+    return check_launch("subsample2_rows_kernel");
+  }
   long long total = (long long)n * (Ho + 2) * (Wo + 2) * (C / 8);
   subsample2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, n, H, W, C / 8, (uint4*)out, Ho, Wo);
   return check_launch("subsample2_kernel");
