@@ -202,145 +202,11 @@ __device__ __noinline__ void roi_bin_generic(const TI* base, const lvcb200_fmap&
   }
 }
 
-// ---------------------------------------------------------------- (2b) two-stage separable pooler (bf16 planes -> bf16 NHWC, 7 x 7)
-// With separable weights a bin is  sum_y Wy[y] * (sum_x Wx[x] * f[y, x]).  The inner sums depend on (pixel row, bin column) only, and
-// neighbouring bin rows read the same pixel rows (a 13-pixel-high proposal has all seven bin rows inside six pixel rows), so the kernel
-// below loads and unpacks every pixel once per bin ROW it touches.  Here a CTA owns a whole RoI:
-//   stage 1: h[y][pw] = sum_x Wx_pw[x] f[y, x]   for every pixel row of the RoI's footprint and every bin column -- each pixel vector is
-//            loaded and unpacked ONCE (eight lanes x 16 bytes = 64 channels per task, thirty-two tasks in flight per CTA);
-//   stage 2: out[ph][pw] = sum_y Wy_ph[y] h[y][pw] / count   out of shared memory (fp32 partial sums, two channels per lane).
-// 64 channels at a time (h is kSep2Rows x 7 x 64 fp32 = 43 KB).  RoIs whose footprint has more pixel rows than kSep2Rows, or whose
-// sample grid exceeds the separable tables, are left to roi_pool_fpn_kernel (which skips the ones taken here): same eligibility rule.
-constexpr int kSep2Rows = 24;
-constexpr int kSep2Default = 24;  // RoIs up to this many footprint rows take the two-stage kernel (LVCB200_POOL_SEP2 overrides; 0 = off)
-
-struct Sep2Span { int ylo, rows; };
-__device__ __forceinline__ Sep2Span sep2_span(const RoiGeom& g, int gh, int H, int P) {
-  const float ystep = g.bin_h / (float)gh;
-  Sep2Span s;
-  s.ylo = make_tap1(g.start_h + .5f * ystep, H).lo;
-  s.rows = make_tap1(g.start_h + (float)(P - 1) * g.bin_h + ((float)(gh - 1) + .5f) * ystep, H).hi - s.ylo + 1;
-  return s;
-}
-__device__ __forceinline__ bool sep2_eligible(bool no_level, int gh, int gw, const RoiGeom& g, int H, int P, int max_rows) {
-  if (no_level || gh < 1 || gw < 1 || gh > kMaxSepGrid || gw > kMaxSepGrid || P != 7) return false;
-  const Sep2Span s = sep2_span(g, gh, H, P);
-  return s.rows >= 1 && s.rows <= max_rows;
-}
-
-__global__ void __launch_bounds__(256)
-roi_pool_sep2_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t R, int sampling_ratio, int canon_size, int canon_level,
-                     int min_level, __nv_bfloat16* __restrict__ out, int64_t out_pitch, int max_rows) {
-  constexpr int P = 7, WS = kMaxSepGrid + 4;
-  extern __shared__ float s2_h[];                       // [kSep2Rows][7][64]
-  __shared__ float sWy[P][WS], sWx[P][WS];
-  __shared__ int s_yb[P], s_ny[P], s_xb[P], s_nx[P];
-  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
-    const float* roi = rois + r * 5;
-    const float rx1 = roi[1], ry1 = roi[2], rx2 = roi[3], ry2 = roi[4];
-    int lvl = 0;
-    if (L.n_levels > 1) lvl = assign_level(rx1, ry1, rx2, ry2, min_level, min_level + L.n_levels - 1, canon_size, canon_level);
-    const bool no_level = lvl < 0;
-    if (no_level) lvl = 0;
-    const lvcb200_fmap fm = L.lv[lvl];
-    const int H = fm.H, W = fm.W;
-    const RoiGeom g = roi_geom(roi, fm.spatial_scale, P, P, sampling_ratio, true);
-    const int gh = g.grid_h, gw = g.grid_w;
-    if (!sep2_eligible(no_level, gh, gw, g, H, P, max_rows)) continue;   // (uniform over the CTA)
-    const Sep2Span span = sep2_span(g, gh, H, P);
-    const float ystep = g.bin_h / (float)gh, xstep = g.bin_w / (float)gw;
-    __syncthreads();                                                   // the previous RoI's stage 2 is done with the tables
-    for (int i = tid; i < P * WS; i += 256) { (&sWy[0][0])[i] = 0.f; (&sWx[0][0])[i] = 0.f; }
-    if (tid < P) {
-      const float y_first = g.start_h + tid * g.bin_h;
-      const int yb = make_tap1(y_first + .5f * ystep, H).lo;
-      s_yb[tid] = yb;
-      s_ny[tid] = make_tap1(y_first + ((float)(gh - 1) + .5f) * ystep, H).hi - yb + 1;
-    } else if (tid >= 32 && tid < 32 + P) {
-      const int pw = tid - 32;
-      const float x_first = g.start_w + pw * g.bin_w;
-      const int xb = make_tap1(x_first + .5f * xstep, W).lo;
-      s_xb[pw] = xb;
-      s_nx[pw] = make_tap1(x_first + ((float)(gw - 1) + .5f) * xstep, W).hi - xb + 1;
-    }
-    __syncthreads();
-    // 1-D weight tables: one warp per table row (the eight warps take the seven rows of Wy and the seven of Wx), so every slot is
-    // accumulated by the lanes of a single warp, like in roi_pool_fpn_kernel
-    for (int row = wib; row < 2 * P; row += 8) {
-      const bool isy = row < P;
-      const int b = isy ? row : row - P;
-      const int gn = isy ? gh : gw, size = isy ? H : W;
-      const float first = isy ? g.start_h + b * g.bin_h : g.start_w + b * g.bin_w, step = isy ? ystep : xstep;
-      const int base0 = isy ? s_yb[b] : s_xb[b];
-      float* tbl = isy ? sWy[b] : sWx[b];
-      if (lane < gn) {
-        const Tap1 t = make_tap1(first + ((float)lane + .5f) * step, size);
-        if (t.valid) { atomicAdd(&tbl[t.lo - base0], t.wlo); atomicAdd(&tbl[t.hi - base0], t.whi); }
-      }
-    }
-    __syncthreads();
-    const float inv_count = 1.0f / g.count;
-    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(fm.base) + (int64_t)roi[0] * fm.img_stride * fm.c_stride;
-    const int cs = (int)fm.c_stride;
-    const int gg = tid >> 3, part = tid & 7;
-    const int T = span.rows * P;
-    for (int cc = 0; cc < C; cc += 64) {
-      // ---- stage 1
-      for (int task = gg; task < T; task += 32) {
-        const int yr = task / P, pw = task - yr * P;
-        const int nx = s_nx[pw];
-        const float* wx = sWx[pw];
-        const __nv_bfloat16* px = base + ((int64_t)(span.ylo + yr) * fm.row_stride + s_xb[pw]) * cs + cc + part * 8;
-        float2 a[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = make_float2(0.f, 0.f);
-        for (int x0 = 0; x0 < nx; x0 += 8) {            // up to eight pixel vectors in flight per lane (footprints are 2..33 pixels wide)
-          uint4 raw[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++)
-            if (x0 + u < nx) raw[u] = __ldg(reinterpret_cast<const uint4*>(px + (int64_t)(x0 + u) * cs));
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            if (x0 + u < nx) {
-              float v[8];
-              Vec<__nv_bfloat16>::unpack(raw[u], v);
-              const float w = wx[x0 + u];
-              const float2 ww = make_float2(w, w);
-#pragma unroll
-              for (int i = 0; i < 4; i++) a[i] = __ffma2_rn(ww, make_float2(v[2 * i], v[2 * i + 1]), a[i]);
-            }
-          }
-        }
-        float4* hp = reinterpret_cast<float4*>(s2_h + ((size_t)task * 64 + part * 8));
-        hp[0] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
-        hp[1] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
-      }
-      __syncthreads();
-      // ---- stage 2: warp w takes bins w, w + 8, ...; lane = two channels
-      for (int bin = wib; bin < P * P; bin += 8) {
-        const int ph = bin / P, pw = bin - ph * P;
-        const int ny = s_ny[ph], y0 = s_yb[ph] - span.ylo;
-        const float* wy = sWy[ph];
-        float2 acc = make_float2(0.f, 0.f);
-        for (int ry = 0; ry < ny; ry++) {
-          const float2 hv = *reinterpret_cast<const float2*>(s2_h + ((size_t)((y0 + ry) * P + pw) * 64 + lane * 2));
-          const float w = wy[ry];
-          acc = __ffma2_rn(make_float2(w, w), hv, acc);
-        }
-        *reinterpret_cast<__nv_bfloat162*>(out + r * out_pitch + (int64_t)bin * C + cc + lane * 2) =
-            __floats2bfloat162_rn(acc.x * inv_count, acc.y * inv_count);
-      }
-      __syncthreads();
-    }
-  }
-}
-
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256, 2)
 roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t R, int P, int sampling_ratio,
                     int canon_size, int canon_level, int min_level, TO* __restrict__ out, int out_layout,
-                    int64_t out_pitch, int64_t* __restrict__ levels_out, int sep2_rows) {
+                    int64_t out_pitch, int64_t* __restrict__ levels_out) {
   constexpr int V = Vec<TI>::N;
   constexpr int MAXP = 8, WS = kMaxSepGrid + 4;
   __shared__ float sWy[8][WS], sWx[8][MAXP][WS];
@@ -364,7 +230,6 @@ roi_pool_fpn_kernel(PoolLevels L, int C, const float* __restrict__ rois, int64_t
     const int H = fm.H, W = fm.W;
     RoiGeom g = roi_geom(roi, fm.spatial_scale, P, P, sampling_ratio, true);
     const int gh = no_level ? 0 : g.grid_h, gw = no_level ? 0 : g.grid_w;
-    if (sep2_rows > 0 && sep2_eligible(no_level, g.grid_h, g.grid_w, g, H, P, sep2_rows)) continue;   // roi_pool_sep2_kernel owns this RoI
     const TI* base = reinterpret_cast<const TI*>(fm.base) + (int64_t)roi[0] * fm.img_stride * fm.c_stride;
     const bool separable = gh >= 1 && gw >= 1 && gh <= kMaxSepGrid && gw <= kMaxSepGrid && P <= MAXP;
     const float inv_count = 1.0f / g.count;
@@ -513,25 +378,10 @@ extern "C" int lvcb200_roi_pool_fpn(const lvcb200_fmap* levels, int n_levels, in
   int64_t blocks = ceil_div64(warps, threads / 32);
   if (blocks > (int64_t)kNumSMs * 256) blocks = (int64_t)kNumSMs * 256;
   cudaStream_t s = (cudaStream_t)stream;
-  // bf16 planes -> bf16 NHWC 7 x 7 (the engine's pooler): RoIs whose footprint spans at most `sep2_rows` pixel rows go through the two-stage
-  // separable kernel, the rest (and every other dtype / layout) through the per-bin-row kernel, which skips the RoIs the first one owns
-  static const char* e_sep2 = getenv("LVCB200_POOL_SEP2");
-  int sep2_rows = e_sep2 ? atoi(e_sep2) : kSep2Default;
-  if (sep2_rows > kSep2Rows) sep2_rows = kSep2Rows;
-  if (!(in_dtype == LVCB200_BF16 && out_dtype == LVCB200_BF16 && out_layout == LVCB200_OUT_NHWC && pooled == 7 && C % 64 == 0 &&
-        ((uintptr_t)out % 4) == 0 && out_pitch % 2 == 0)) sep2_rows = 0;
-  if (sep2_rows > 0) {
-    const int64_t ctas = R < (int64_t)kNumSMs * 4 ? R : (int64_t)kNumSMs * 4;
-    roi_pool_sep2_kernel<<<(unsigned)ctas, 256, kSep2Rows * 7 * 64 * sizeof(float), s>>>(L, C, rois, R, sampling_ratio, canonical_box_size,
-                                                                                        canonical_level, min_level, (__nv_bfloat16*)out, out_pitch,
-                                                                                        sep2_rows);
-    int rc = check_launch("roi_pool_sep2_kernel");
-    if (rc) return rc;
-  }
 #define LAUNCH(TI, TO)                                                                                              \
   roi_pool_fpn_kernel<TI, TO><<<(unsigned)blocks, threads, 0, s>>>(L, C, rois, R, pooled, sampling_ratio,           \
                                                                    canonical_box_size, canonical_level, min_level, \
-                                                                   (TO*)out, out_layout, out_pitch, levels_out, sep2_rows)
+                                                                   (TO*)out, out_layout, out_pitch, levels_out)
   if (in_dtype == LVCB200_BF16 && out_dtype == LVCB200_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == LVCB200_BF16 && out_dtype == LVCB200_F32) LAUNCH(__nv_bfloat16, float);
   else if (in_dtype == LVCB200_F32 && out_dtype == LVCB200_F32) LAUNCH(float, float);
