@@ -481,8 +481,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 [[maybe_unused]] const uint32_t* uw = &ut.x;
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                  float a0 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e]) + bb[2 * e];
-                  float a1 = __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1]) + bb[2 * e + 1];
+                  const float2 ab = __fadd2_rn(make_float2(__uint_as_float(v[g2 * 32 + 8 * j + 2 * e]), __uint_as_float(v[g2 * 32 + 8 * j + 2 * e + 1])),
+                                               make_float2(bb[2 * e], bb[2 * e + 1]));      // one FADD2 (rounds each half like FADD)
+                  float a0 = ab.x, a1 = ab.y;
                   if constexpr (UPS) { a0 += __uint_as_float(uw[e] << 16); a1 += __uint_as_float(uw[e] & 0xffff0000u); }
                   if constexpr (ACT == 1) {
                     const float2 gg = gelu_erf2(make_float2(a0, a1));
