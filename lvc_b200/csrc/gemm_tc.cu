@@ -447,6 +447,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       } else {
         const int r = q * 32 + lane;
         const int sw = r & 7;                           // SWIZZLE_128B: 16-byte chunk index ^= row & 7
+        const bool relu_f = ACT == 0 && p.relu != 0;
         const int cols_per_warp = p.phase_cols >> 1;    // 32 (phase 64) or 64 (phase 128)
 #pragma unroll 1
         for (int pcs = 0; pcs < BLOCK_N * kSplitPasses; pcs += p.phase_cols) {
@@ -488,7 +489,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   if constexpr (ACT == 1) {
                     const float2 gg = gelu_erf2(make_float2(a0, a1));
                     a0 = gg.x; a1 = gg.y;
-                  } else if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                  }
+                  if constexpr (!SPLIT && ACT == 0) {
+                    // plain bf16 / fp16 output: ReLU rides the conversion (cvt.rn.relu.bf16x2.f32), border rows are zeroed on the packed word
+                    uint32_t pk;
+                    if (p.d_f16) {
+                      if (relu_f) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                      const __half2 hh = __floats2half2_rn(a0, a1);
+                      pk = *reinterpret_cast<const uint32_t*>(&hh);
+                    } else if (relu_f) {
+                      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(a1), "f"(a0));
+                    } else {
+                      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(a1), "f"(a0));
+                    }
+                    (&o.x)[e] = zero_row ? 0u : pk;
+                    continue;
+                  }
+                  if (relu_f) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
                   if (zero_row) { a0 = 0.f; a1 = 0.f; }
                   if constexpr (SPLIT) {
                     const __nv_bfloat162 hi2 = __floats2bfloat162_rn(a0, a1);
