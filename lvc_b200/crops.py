@@ -1,6 +1,6 @@
 """Crop front end of the kNN descriptors (the part that is index arithmetic): the mirror of
 ``get_crops_qe`` (lvc/data/utils.py:485-519) and ``preprocess_crops`` (tools/run_nearest_neighbours.py:102-105).
-The DINO ViT forward that consumes the crops is not part of this round."""
+The DINO ViT forward that consumes the crops is lvc_b200.modeling.DinoViT (lvc_b200.knn.get_descriptors chains the two)."""
 import numpy as np
 import torch
 

@@ -9,7 +9,9 @@
 //   layernorm_kernel      : warp per row, fp32 statistics, bf16 or fp32 output, arbitrary row pitch (the final norm reads CLS rows only)
 //   gelu_kernel           : exact (erf) GELU in place on bf16
 //   attention_kernel      : fused softmax(Q K^T / sqrt(d)) V for head_dim 64 on mma.sync (flash-style: 64 queries per CTA, K / V streamed in
-//                           64-key blocks through cp.async double buffers, online softmax in registers, P re-used as the A fragment)
+//                           64-key blocks through cp.async double buffers, online softmax in registers, P re-used as the A fragment).
+//                           The default attention of DinoViT is the tcgen05 / TMEM kernel of attention_tc.cu; this one stays selectable.
+//   *8 / *_reg variants   : 16-byte fast paths of patchify / assemble (patch 8, D % 8 == 0) and LayerNorm with the row in registers (D = 384)
 #include <cuda_fp16.h>
 
 #include "common.cuh"
