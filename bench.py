@@ -191,8 +191,8 @@ def knn_section(rank, world, dev, dist, with_cpu):
     queries = torch.randn(qh - ql, D, generator=g2, device=dev) + means[qcls]
     res = {}
 
-    def step(path):
-        c, b = all_gather_bank(cls_all[lo:hi], bank_all[lo:hi], total=S)  # the one exchange step: a single all_gather, no host sync
+    def step(path, backend="nccl"):
+        c, b = all_gather_bank(cls_all[lo:hi], bank_all[lo:hi], total=S, backend=backend)  # the one exchange step: a single all_gather, no host sync
         kb = ops.KnnBank(b, c)
         return kb.verify(queries, qcls, topk=10, knn=10, path=path)
 
@@ -239,6 +239,26 @@ def knn_section(rank, world, dev, dist, with_cpu):
             res["tc"]["graph_keep_fraction_rank0"] = float(gout["keep"].float().mean())
     except Exception as e:  # noqa: BLE001
         res["tc"]["graph_replay_error"] = repr(e)
+    # the same with the bank exchanged by lvcb200_gather_rows_p2p over NVLink peer memory (torch symmetric memory + device-side barrier)
+    # instead of the NCCL all-gather
+    if world > 1 and os.environ.get("LVCB200_BENCH_KNN_P2P", "1") != "0":
+        try:
+            ref_keep = step("tc")["keep"].clone()
+            for _ in range(2):
+                p2p_out = step("tc", "p2p")
+            same = bool(torch.equal(p2p_out["keep"], ref_keep))
+            ms_p, _ = timed(lambda: step("tc", "p2p"), 4)
+            res["tc"]["p2p_exchange"] = {"eager_ms": ms_p, "identical_to_nccl_path": same}
+            g2 = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            dist.barrier()
+            with torch.cuda.graph(g2):               # TWO calls per graph: the exchange alternates between two symmetric buffers, and a
+                step("tc", "p2p")                    # replay must not rewrite the buffer a slower peer may still be reading
+                step("tc", "p2p")
+            ms_pg, _ = timed(lambda: g2.replay(), 5)
+            res["tc"]["p2p_exchange"]["graph_replay_ms"] = ms_pg / 2
+        except Exception as e:  # noqa: BLE001
+            res["tc"].setdefault("p2p_exchange", {})["error"] = repr(e)[:300]
     peak_tf, peak_hbm, which, _ = measured_peaks()
     best_gbs = res["tc"].get("graph_replay_hbm_gbs", res["tc"]["hbm_gbs"])
     res["tc"]["kernels"] = "knn_split_queries (fp32 -> bf16 hi/lo pair) + knn_tc3 (tcgen05 3-term product, top-14 in the TMEM epilogue) + knn_resolve (exact re-scoring of uncertain queries)"

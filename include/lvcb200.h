@@ -345,6 +345,12 @@ int lvcb200_match_boxes(const float* gt_boxes, int64_t G, const float* boxes, co
                         int allow_low_quality_matches, int64_t* matches, int8_t* match_labels, float* matched_vals, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* The bank exchange of the kNN (tools/run_nearest_neighbours.py:303-309) over NVLink peer memory instead of an NCCL launch: peer_bufs[r]
+ * (HOST array of W <= 16 device pointers, every rank's padded shard [1 + cap, row_floats] fp32 mapped into this process, e.g. torch symmetric
+ * memory) -> out [sum rows, row_floats], rank-major; row 0 of every shard (the header) is skipped.  The caller orders the reads behind the
+ * peers' writes (device-side barrier).  rows: HOST [W]. */
+int lvcb200_gather_rows_p2p(const void* const* peer_bufs, int W, const int32_t* rows, int row_floats, void* out, void* stream);
+
 /* subsample_labels (detectron2/modeling/sampling.py:9-54) for n_vectors label vectors [n_vectors, N] (int64, or int8 when
  * labels_are_int8) with the two torch.randperm draws replaced by caller-supplied random keys [n_vectors, N] uint32: the positives
  * (label != -1 && != bg_label) / negatives (== bg_label) with the smallest (key, index) pairs are taken, in that order

@@ -93,6 +93,7 @@ _SIGS = {
     "lvcb200_match_boxes_workspace": (c_size_t, [c_int64]),
     "lvcb200_match_boxes": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, POINTER(c_float), c_int, POINTER(ctypes.c_int8), c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lvcb200_gather_rows_p2p": (c_int, [POINTER(c_void_p), c_int, POINTER(ctypes.c_int32), c_int, c_void_p, c_void_p]),
     "lvcb200_subsample_labels": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, ctypes.c_double, c_int64, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p]),
     "lvcb200_rpn_losses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(c_float), c_float, c_void_p,

@@ -350,6 +350,20 @@ crops_qe4_kernel(const T* __restrict__ img, int H, int W, const CropGeom* __rest
   }
 }
 
+// The bank exchange of the kNN (run_nearest_neighbours.py:303-309) by our own kernel over NVLink peer memory: every rank has written
+// its padded shard [1 + cap, row_floats] (header row first) into a buffer that is mapped into all ranks (torch symmetric memory); after the
+// device-side barrier this kernel reads the peers' rows with plain loads through NVLink / NVSwitch and writes the rank-major concatenation
+// [total, row_floats] locally -- no NCCL launch, no staging copy.  blockIdx.y = source rank.
+struct PeerRows { const float* buf[16]; int rows[16]; int offset[16]; };
+__global__ void __launch_bounds__(256)
+gather_rows_p2p_kernel(PeerRows pr, int row_floats, float* __restrict__ out) {
+  const int r = blockIdx.y;
+  const long long nv = (long long)pr.rows[r] * row_floats / 2;                 // float2 vectors (row_floats is even: D + 2)
+  const float2* src = reinterpret_cast<const float2*>(pr.buf[r] + row_floats);   // skip the header row
+  float2* dst = reinterpret_cast<float2*>(out + (long long)pr.offset[r] * row_floats);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace lvcb200
 
 using namespace lvcb200;
@@ -499,4 +513,26 @@ extern "C" int lvcb200_crops_qe(const void* image, int image_dtype, int H, int W
   else
     return set_error(LVCB200_EINVAL, "crops_qe: image dtype must be LVCB200_F32 or LVCB200_U8");
   return check_launch("crops_qe_kernel");
+}
+
+extern "C" int lvcb200_gather_rows_p2p(const void* const* peer_bufs /*host array of W device pointers*/, int W, const int32_t* rows /*host [W]*/,
+                                       int row_floats, void* out, void* stream) {
+  LVC_REQUIRE(W >= 1 && W <= 16 && peer_bufs && rows && out && row_floats >= 2 && row_floats % 2 == 0, "gather_rows_p2p: bad argument (at most 16 ranks)");
+  PeerRows pr;
+  int off = 0, most = 0;
+  for (int r = 0; r < 16; r++) { pr.buf[r] = nullptr; pr.rows[r] = 0; pr.offset[r] = 0; }
+  for (int r = 0; r < W; r++) {
+    LVC_REQUIRE(peer_bufs[r] && rows[r] >= 0 && ((uintptr_t)peer_bufs[r] % 8) == 0, "gather_rows_p2p: NULL / misaligned peer buffer");
+    pr.buf[r] = (const float*)peer_bufs[r]; pr.rows[r] = rows[r]; pr.offset[r] = off;
+    off += rows[r];
+    most = rows[r] > most ? rows[r] : most;
+  }
+  if (off == 0) return 0;
+  LVC_REQUIRE(((uintptr_t)out % 8) == 0, "gather_rows_p2p: out must be 8-byte aligned");
+  const long long nv = (long long)most * row_floats / 2;
+  unsigned gx = (unsigned)((nv + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  gather_rows_p2p_kernel<<<dim3(gx, W), 256, 0, (cudaStream_t)stream>>>(pr, row_floats, (float*)out);
+  return check_launch("gather_rows_p2p_kernel");
 }

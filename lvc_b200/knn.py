@@ -25,7 +25,8 @@ def assemble_tensors(shot_features: List[dict]) -> Tuple[torch.Tensor, torch.Ten
     return classes[sorter], desc[sorter]
 
 
-def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None, total: Optional[int] = None):
+def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None, total: Optional[int] = None,
+                    backend: str = "nccl"):
     """The ONE exchange step of the path (run_nearest_neighbours.py:303-309): every rank ends with the full bank,
     rank-major order (== torch.cat(comm.all_gather(...))).
 
@@ -34,7 +35,15 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
     shard is padded to ``ceil(total / W)`` rows, and the exchange is a SINGLE ``all_gather_into_tensor`` of one
     ``[1 + ceil(total/W), D + 2]`` fp32 block per rank -- descriptors, bit-cast int64 classes, and a header row carrying the
     shard's row count -- with no host synchronisation anywhere (sizes are not read back: the header only feeds a device-side
-    consistency flag, ``all_gather_bank.last_check``).  Without ``total`` (arbitrary uneven shards) a size exchange comes first."""
+    consistency flag, ``all_gather_bank.last_check``).  Without ``total`` (arbitrary uneven shards) a size exchange comes first.
+
+    ``backend="p2p"`` (CUDA, needs ``total``): no NCCL launch at all -- the padded block is written into a buffer that torch's symmetric
+    memory maps into every rank, a device-side barrier orders the reads behind the writes, and ``lvcb200_gather_rows_p2p`` pulls the peers'
+    rows over NVLink / NVSwitch with plain loads straight into the concatenated bank (``all_gather_bank_p2p``)."""
+    if backend == "p2p":
+        return all_gather_bank_p2p(shot_classes, shot_descriptors, group, total)
+    if backend != "nccl":
+        raise ValueError("all_gather_bank: backend must be 'nccl' or 'p2p'")
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return shot_classes, shot_descriptors
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -72,6 +81,61 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
 
 
 all_gather_bank.last_check = None
+
+_P2P_STATE = {}   # (group id, cap, D) -> [symmetric buffers (two, used alternately), handles, call counter]
+
+
+def all_gather_bank_p2p(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None, total: Optional[int] = None):
+    """``all_gather_bank`` over NVLink peer memory (see there).  Two symmetric buffers are used alternately so that ONE device-side
+    barrier per call suffices: a rank that passes the barrier of call n + 1 has finished its reads of call n (stream order), so buffer
+    n mod 2 may be rewritten in call n + 2.  The first call for a (group, size) pair allocates and rendezvouses the buffers (a
+    collective, host-synchronising step); later calls are stream-ordered and CUDA-graph capturable."""
+    import ctypes
+
+    import torch.distributed._symmetric_memory as symm
+
+    from . import _lib
+    from .evaluation import inference_shard
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return shot_classes, shot_descriptors
+    if total is None:
+        raise ValueError("all_gather_bank_p2p needs `total` (the shard sizes follow from the InferenceSampler rule)")
+    _lib.require_cuda(shot_descriptors, shot_classes)
+    grp = group if group is not None else dist.group.WORLD
+    world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+    if world > 16:
+        raise _lib.LvcB200Error("all_gather_bank_p2p: at most 16 ranks (one NVLink domain)")
+    dev = shot_descriptors.device
+    D, n_mine = shot_descriptors.shape[1], shot_descriptors.shape[0]
+    sizes = [len(inference_shard(total, r, world)) for r in range(world)]
+    if sizes[rank] != n_mine:
+        raise ValueError(f"all_gather_bank_p2p: rank {rank} holds {n_mine} rows, the InferenceSampler rule gives {sizes[rank]} of {total}")
+    cap = max(sizes)
+    key = (id(grp), cap, D, dev.index)
+    st = _P2P_STATE.get(key)
+    if st is None:
+        bufs = [symm.empty((cap + 1, D + 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        hdls = [symm.rendezvous(b, grp) for b in bufs]
+        for b in bufs:
+            b.zero_()
+        st = _P2P_STATE[key] = [bufs, hdls, 0]
+        torch.cuda.synchronize(dev)
+        dist.barrier(grp)
+    bufs, hdls, n = st
+    st[2] = n + 1
+    pack, hdl = bufs[n & 1], hdls[n & 1]
+    pack[0, :1].fill_(float(n_mine))
+    pack[1:1 + n_mine, :D] = shot_descriptors.float()
+    if n_mine:
+        pack[1:1 + n_mine, D:] = shot_classes.to(torch.int64).view(-1, 1).view(torch.float32).view(-1, 2)
+    hdl.barrier()                                         # every rank's shard is in its buffer (device-side, on the current stream)
+    out = torch.empty((total, D + 2), dtype=torch.float32, device=dev)
+    ptrs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs[:world]])
+    rows = (ctypes.c_int32 * world)(*sizes)
+    _lib.check(_lib.load().lvcb200_gather_rows_p2p(ptrs, world, rows, D + 2, _lib.ptr(out), _lib.stream_ptr()), "lvcb200_gather_rows_p2p")
+    desc = out[:, :D].contiguous()
+    cls = out[:, D:].contiguous().view(torch.int64).view(-1)
+    return cls, desc
 
 
 def get_descriptors(model, image, boxes, mean, std, operation="context", size=224):
