@@ -26,7 +26,7 @@ def assemble_tensors(shot_features: List[dict]) -> Tuple[torch.Tensor, torch.Ten
 
 
 def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None, total: Optional[int] = None,
-                    backend: str = "nccl"):
+                    backend: str = "auto"):
     """The ONE exchange step of the path (run_nearest_neighbours.py:303-309): every rank ends with the full bank,
     rank-major order (== torch.cat(comm.all_gather(...))).
 
@@ -37,13 +37,17 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
     shard's row count -- with no host synchronisation anywhere (sizes are not read back: the header only feeds a device-side
     consistency flag, ``all_gather_bank.last_check``).  Without ``total`` (arbitrary uneven shards) a size exchange comes first.
 
+    ``backend="auto"`` (default) takes the peer-memory route below when it is available on every rank (CUDA tensors, ``total`` given,
+    at most 16 ranks, symmetric memory rendezvous succeeded -- agreed on once per (group, size) with an all-reduce) and NCCL otherwise.
     ``backend="p2p"`` (CUDA, needs ``total``): no NCCL launch at all -- the padded block is written into a buffer that torch's symmetric
     memory maps into every rank, a device-side barrier orders the reads behind the writes, and ``lvcb200_gather_rows_p2p`` pulls the peers'
     rows over NVLink / NVSwitch with plain loads straight into the concatenated bank (``all_gather_bank_p2p``)."""
     if backend == "p2p":
         return all_gather_bank_p2p(shot_classes, shot_descriptors, group, total)
-    if backend != "nccl":
-        raise ValueError("all_gather_bank: backend must be 'nccl' or 'p2p'")
+    if backend not in ("nccl", "auto"):
+        raise ValueError("all_gather_bank: backend must be 'auto', 'nccl' or 'p2p'")
+    if backend == "auto" and _p2p_usable(shot_descriptors, group, total):
+        return all_gather_bank_p2p(shot_classes, shot_descriptors, group, total)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return shot_classes, shot_descriptors
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -83,16 +87,63 @@ def all_gather_bank(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, 
 all_gather_bank.last_check = None
 
 _P2P_STATE = {}   # (group id, cap, D) -> [symmetric buffers (two, used alternately), handles, call counter]
+_P2P_OK = {}      # (group id, cap, D, device) -> bool: every rank could set the peer-memory exchange up
+
+
+def _p2p_usable(shot_descriptors: torch.Tensor, group, total) -> bool:
+    """Whether all_gather_bank_p2p can serve this call -- decided collectively the first time a (group, size) pair is seen (every rank
+    tries the symmetric-memory set-up, an all-reduce takes the minimum), never during a CUDA-graph capture of an unseen pair."""
+    import os
+    if total is None or not shot_descriptors.is_cuda or os.environ.get("LVCB200_KNN_P2P", "1") == "0":
+        return False
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    grp = group if group is not None else dist.group.WORLD
+    world = dist.get_world_size(grp)
+    if world == 1 or world > 16 or dist.get_backend(grp) != "nccl":
+        return False
+    from .evaluation import inference_shard
+    cap = max(len(inference_shard(total, r, world)) for r in range(world))
+    key = (id(grp), cap, shot_descriptors.shape[1], shot_descriptors.device.index)
+    if key in _P2P_OK:
+        return _P2P_OK[key]
+    if torch.cuda.is_current_stream_capturing():
+        return False
+    ok = 1
+    try:
+        _p2p_state(grp, cap, shot_descriptors.shape[1], shot_descriptors.device)
+    except Exception:  # noqa: BLE001  (no symmetric memory on this platform / build: every rank falls back to NCCL together)
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=shot_descriptors.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=grp)
+    _P2P_OK[key] = bool(int(flag.item()))
+    return _P2P_OK[key]
+
+
+def _p2p_state(grp, cap, D, dev):
+    """Two symmetric buffers [1 + cap, D + 2] (used alternately) and their handles for this (group, size) pair; allocated and
+    rendezvoused on first use (a collective, host-synchronising step)."""
+    import torch.distributed._symmetric_memory as symm
+    key = (id(grp), cap, D, dev.index)
+    st = _P2P_STATE.get(key)
+    if st is None:
+        bufs = [symm.empty((cap + 1, D + 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        hdls = [symm.rendezvous(b, grp) for b in bufs]
+        for b in bufs:
+            b.zero_()
+        st = _P2P_STATE[key] = [bufs, hdls, 0]
+        torch.cuda.synchronize(dev)
+        dist.barrier(grp)
+    return st
 
 
 def all_gather_bank_p2p(shot_classes: torch.Tensor, shot_descriptors: torch.Tensor, group=None, total: Optional[int] = None):
     """``all_gather_bank`` over NVLink peer memory (see there).  Two symmetric buffers are used alternately so that ONE device-side
     barrier per call suffices: a rank that passes the barrier of call n + 1 has finished its reads of call n (stream order), so buffer
-    n mod 2 may be rewritten in call n + 2.  The first call for a (group, size) pair allocates and rendezvouses the buffers (a
-    collective, host-synchronising step); later calls are stream-ordered and CUDA-graph capturable."""
+    n mod 2 may be rewritten in call n + 2.  The first call for a (group, size) pair allocates and rendezvouses the buffers; later
+    calls are stream-ordered and CUDA-graph capturable (a captured call adds a second barrier in front of the write, because every
+    replay reuses the buffer chosen at capture time)."""
     import ctypes
-
-    import torch.distributed._symmetric_memory as symm
 
     from . import _lib
     from .evaluation import inference_shard
@@ -110,20 +161,12 @@ def all_gather_bank_p2p(shot_classes: torch.Tensor, shot_descriptors: torch.Tens
     sizes = [len(inference_shard(total, r, world)) for r in range(world)]
     if sizes[rank] != n_mine:
         raise ValueError(f"all_gather_bank_p2p: rank {rank} holds {n_mine} rows, the InferenceSampler rule gives {sizes[rank]} of {total}")
-    cap = max(sizes)
-    key = (id(grp), cap, D, dev.index)
-    st = _P2P_STATE.get(key)
-    if st is None:
-        bufs = [symm.empty((cap + 1, D + 2), dtype=torch.float32, device=dev) for _ in range(2)]
-        hdls = [symm.rendezvous(b, grp) for b in bufs]
-        for b in bufs:
-            b.zero_()
-        st = _P2P_STATE[key] = [bufs, hdls, 0]
-        torch.cuda.synchronize(dev)
-        dist.barrier(grp)
+    st = _p2p_state(grp, max(sizes), D, dev)
     bufs, hdls, n = st
     st[2] = n + 1
     pack, hdl = bufs[n & 1], hdls[n & 1]
+    if torch.cuda.is_current_stream_capturing():
+        hdl.barrier()        # a captured call is replayed on the SAME buffer every time: wait until the peers have read the previous replay
     pack[0, :1].fill_(float(n_mine))
     pack[1:1 + n_mine, :D] = shot_descriptors.float()
     if n_mine:

@@ -21,7 +21,7 @@ for total, D in ((600, 1024), (7, 384), (2393, 384), (world, 64)):
     sh = inference_shard(total, rank, world)
     for it in range(3):
         d_in = desc[sh.start:sh.stop] + it
-        c0, d0 = all_gather_bank(cls[sh.start:sh.stop], d_in, total=total)
+        c0, d0 = all_gather_bank(cls[sh.start:sh.stop], d_in, total=total, backend="nccl")
         c1, d1 = all_gather_bank(cls[sh.start:sh.stop], d_in, total=total, backend="p2p")
         same = torch.equal(c0, c1) and torch.equal(d0, d1) and torch.equal(d1, desc + it) and torch.equal(c1, cls)
         ok = ok and same
