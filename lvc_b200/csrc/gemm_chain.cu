@@ -401,14 +401,15 @@ gemm_chain_kernel(const ChainLayer* __restrict__ layers, const uint32_t* __restr
             b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + 8 * j + 4));
           }
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+          uint4 o;
 #pragma unroll
           for (int e2 = 0; e2 < 4; e2++) {
-            float a0 = __uint_as_float(v[8 * j + 2 * e2]) + bb[2 * e2];
-            float a1 = __uint_as_float(v[8 * j + 2 * e2 + 1]) + bb[2 * e2 + 1];
+            const float2 ab = __fadd2_rn(make_float2(__uint_as_float(v[8 * j + 2 * e2]), __uint_as_float(v[8 * j + 2 * e2 + 1])),
+                                         make_float2(bb[2 * e2], bb[2 * e2 + 1]));      // one FADD2 (rounds each half like FADD)
+            float a0 = ab.x, a1 = ab.y;
             if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            if (zero_row) { a0 = 0.f; a1 = 0.f; }
-            ho[e2] = __floats2bfloat162_rn(a0, a1);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+            (&o.x)[e2] = zero_row ? 0u : *reinterpret_cast<const uint32_t*>(&h2);      // border rows zeroed on the packed word
           }
           *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) = o;
         }
