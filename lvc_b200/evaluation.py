@@ -158,6 +158,47 @@ class CandidateCollector(DatasetEvaluator):
                 "num_candidates": sum(1 for a in anns if a["ignore_qe"] == 0)}
 
 
+class PseudoLabelCollector(DatasetEvaluator):
+    """End of the chained pipeline (``lvc_b200.mining.PseudoLabelMiner``): consumes results that carry ``pseudo_labels`` (the verified, and
+    if a corrector ran corrected, boxes in the output frame) and emits them as the annotation list the reference's last stage writes
+    (tools/train_net_reg_qe.py -> ``UBBRSaver``: COCO-style dicts with ``image_id``, ``category_id``, XYWH ``bbox``, ``score``, ``area``,
+    ``iscrowd`` 0 and a running ``id``).  Ranks gather in rank order (== ``chain(*comm.gather(...))``): with ``inference_shard`` that is
+    dataset order.  Also counts what went through the stages (detections, candidates, verified)."""
+
+    def __init__(self, contiguous_id_to_dataset_id=None):
+        self._map = contiguous_id_to_dataset_id
+        self._records = []
+
+    def reset(self):
+        self._records = []
+
+    def process(self, inputs, outputs):
+        for inp, out in zip(inputs, outputs):
+            pl = out["pseudo_labels"]
+            rows = instances_to_coco_json(pl, inp["image_id"]) if len(pl.pred_boxes) else []
+            n_det = len(out["instances"]) if "instances" in out else 0
+            n_cand = len(out["candidates"].gt_boxes) if "candidates" in out else 0
+            self._records.append((inp["image_id"], n_det, n_cand, rows))
+
+    def evaluate(self):
+        recs = self._records
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+            dist.gather_object(recs, gathered, dst=0)
+            if dist.get_rank() != 0:
+                return {}
+            recs = list(itertools.chain(*gathered))
+        anns = []
+        for image_id, n_det, n_cand, rows in recs:
+            for d in rows:
+                d.update(id=len(anns) + 1, area=d["bbox"][2] * d["bbox"][3], iscrowd=0)
+                if self._map is not None:
+                    d["category_id"] = self._map[d["category_id"]]
+                anns.append(d)
+        return {"num_images": len(recs), "num_detections": sum(r[1] for r in recs), "num_candidates": sum(r[2] for r in recs),
+                "num_pseudo_labels": len(anns), "annotations": anns}
+
+
 def inference_shard(n, rank=None, world_size=None):
     """The reference's InferenceSampler rule (detectron2/data/samplers/distributed_sampler.py:191-194): rank r of W takes the
     contiguous block [r * ceil(n / W), min((r + 1) * ceil(n / W), n)) -- so that chain(*gather(...)) on rank 0 is in dataset order.

@@ -248,6 +248,10 @@ class PseudoLabelMiner:
     def __call__(self, batched_inputs: List[dict]) -> List[dict]:
         return self._finish(self._correct(self._verify(self._label(batched_inputs))))
 
+    def inference_stream(self, batches):
+        """The name ``lvc_b200.evaluation.inference_on_dataset`` looks for: ``inference_on_dataset(miner, loader, PseudoLabelCollector())``."""
+        return self.stream(batches)
+
     @torch.no_grad()
     def stream(self, batches):
         """``miner(inputs)`` for every batch of the iterable, in order, software-pipelined: while the GPU runs the detector on batch i

@@ -86,3 +86,54 @@ def test_sharded_mining_gathers_in_dataset_order_gloo_world2():
     assert ret[1][1] is None                                              # only rank 0 holds the gathered results
     want = [i for i in range(7) for _ in range(1 + i % 3)]               # every detection, in dataset order
     assert ret[0][1] == 7 and ret[0][2] == want
+
+
+# ---------------------------------------------------------------- the chained pipeline's collector (stub miner, gloo world 2)
+class _StubMiner:
+    """Stands in for lvc_b200.mining.PseudoLabelMiner: per image 1 + id % 3 detections, the first id % 2 of them verified.  Has the
+    ``inference_stream`` entry point inference_on_dataset looks for."""
+
+    def __call__(self, batch):
+        out = []
+        for x in batch:
+            inst = _inst(1 + x["image_id"] % 3, seed=x["image_id"])
+            k = x["image_id"] % 2
+            pl = Instances(inst.image_size)
+            pl.pred_boxes = Boxes(inst.pred_boxes.tensor[:k].clone())
+            pl.pred_classes, pl.scores = inst.pred_classes[:k], inst.scores[:k]
+            cand = Instances(inst.image_size)
+            cand.gt_boxes = Boxes(inst.pred_boxes.tensor[:1].clone())
+            out.append({"instances": inst, "candidates": cand, "pseudo_labels": pl})
+        return out
+
+    def inference_stream(self, batches):
+        for b in batches:
+            yield self(b)
+
+
+def _miner_worker(rank, world, port, n_images, ret):
+    import torch.distributed as dist
+    from lvc_b200.evaluation import PseudoLabelCollector, inference_shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = inference_shard(n_images)
+    batches = [[{"image_id": i} for i in list(mine)[j:j + 2]] for j in range(0, len(mine), 2)]
+    out = inference_on_dataset(_StubMiner(), iter(batches), PseudoLabelCollector({c: c + 1 for c in range(80)}))
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_pseudo_label_collector_gathers_in_dataset_order_gloo_world2():
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + 11
+    ret = mp.Manager().dict()
+    mp.spawn(_miner_worker, args=(2, port, 9, ret), nprocs=2, join=True)
+    assert ret[1] == {}
+    r = ret[0]
+    assert r["num_images"] == 9 and r["num_detections"] == sum(1 + i % 3 for i in range(9)) and r["num_candidates"] == 9
+    anns = r["annotations"]
+    assert [a["image_id"] for a in anns] == [1, 3, 5, 7] and [a["id"] for a in anns] == [1, 2, 3, 4] and r["num_pseudo_labels"] == 4
+    want = instances_to_coco_json(_inst(2, seed=1), 1)[0]
+    a = anns[0]
+    assert a["bbox"] == pytest.approx(want["bbox"]) and a["category_id"] == want["category_id"] + 1 and a["iscrowd"] == 0
+    assert a["area"] == pytest.approx(a["bbox"][2] * a["bbox"][3])

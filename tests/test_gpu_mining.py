@@ -160,3 +160,17 @@ def test_miner_stream_equals_blocking_calls():
             n_cand += len(r["candidates"])
     assert n_cand > 0
     assert list(miner.stream([])) == []
+    # the same run through the reference-style driver: inference_on_dataset(miner, loader, PseudoLabelCollector())
+    from lvc_b200.evaluation import PseudoLabelCollector, inference_on_dataset
+    res = inference_on_dataset(miner, iter(batches), PseudoLabelCollector())
+    n_pl = sum(len(w["pseudo_labels"].pred_boxes) for wb in want for w in wb)
+    assert res["num_images"] == 2 * len(batches) and res["num_pseudo_labels"] == n_pl and res["num_candidates"] == n_cand
+    flat = [w for wb in want for w in wb]
+    k = 0
+    for w, x in zip(flat, [x for b in batches for x in b]):
+        for j in range(len(w["pseudo_labels"].pred_boxes)):
+            a = res["annotations"][k]
+            bx = w["pseudo_labels"].pred_boxes.tensor[j]
+            assert a["image_id"] == x["image_id"] and a["category_id"] == int(w["pseudo_labels"].pred_classes[j])
+            assert abs(a["bbox"][0] - float(bx[0])) < 1e-4 and abs(a["bbox"][2] - float(bx[2] - bx[0])) < 1e-3
+            k += 1
